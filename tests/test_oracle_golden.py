@@ -1,0 +1,109 @@
+"""Pins oracle/ (the CPU restatement) against the golden vectors produced by the unmodified
+reference (tests/golden/make_golden.py) and the SURVEY.md §4 known answers.  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import decode as odecode
+from oracle import melbank
+from oracle import model as omodel
+from some_b200 import synth
+
+
+def test_melbank_known_answers(golden_dir):
+    w = melbank.mel_filterbank(44100, 2048, 80, 40, 8000)
+    assert w.shape == (80, 1025) and w.dtype == np.float32
+    assert abs(float(w.sum()) - 3.716216) < 1e-5
+    assert abs(float(w.max()) - 0.041265) < 1e-6
+    assert int((w != 0).sum()) == 727
+    nz = np.nonzero(w.sum(0))[0]
+    assert (nz[0], nz[-1]) == (2, 371)
+    assert int((w != 0).sum(0).max()) == 2
+    ref = np.load(golden_dir / 'mel.npz')['mel_basis']     # buffer of the reference's MelSpectrogram
+    assert np.array_equal(w, ref)
+    import torchaudio
+    ta = torchaudio.functional.melscale_fbanks(1025, 40, 8000, 80, 44100, norm='slaney', mel_scale='htk').T.numpy()
+    assert np.abs(w - ta).max() < 2e-7                      # independent implementation
+
+
+def test_log_mel_matches_reference(golden_dir):
+    g = np.load(golden_dir / 'mel.npz')
+    clips = synth.edge_case_waveforms()
+    clips['sung3s'] = synth.synth_waveform(101, seconds=3.0)
+    for name, w in clips.items():
+        ref = g['mel_' + name]
+        got = omodel.log_mel(torch.from_numpy(w).unsqueeze(0))[0].numpy()
+        assert got.shape == ref.shape == (80, synth.frames_of(len(w))), name
+        np.testing.assert_allclose(got, ref, rtol=0, atol=2e-4, err_msg=name)
+    assert np.all(g['mel_zeros'] == np.float32(np.log(np.float32(1e-5))))   # silence -> log(clamp)
+
+
+def test_decode_known_answers(golden_dir):
+    g = np.load(golden_dir / 'decode_kat.npz')
+    for b in range(2):
+        f2i, vals = g['ex_frame2item'][b], g['ex_values'][b]
+        iv, idur, im = odecode.decode_note_sequence(f2i, vals, f2i > 0)
+        n = int(f2i.max())
+        np.testing.assert_array_equal(iv, g['ex_item_values'][b][:n])
+        np.testing.assert_array_equal(idur, g['ex_item_dur'][b][:n])
+        np.testing.assert_array_equal(im, g['ex_item_masks'][b][:n])
+    # the published expectations themselves
+    np.testing.assert_array_equal(g['ex_item_values'], [[60.25, 57, 50, 0], [50.25, 53, 47, 38]])
+    np.testing.assert_array_equal(g['ex_item_dur'], [[4, 2, 3, 0], [3, 1, 5, 2]])
+    np.testing.assert_array_equal(odecode.decode_bounds_to_alignment(g['kat_bounds'][0]), g['kat_frame2item'][0])
+    np.testing.assert_array_equal(g['kat_frame2item'][0], [1, 1, 1, 2, 2, 2, 2, 3, 4, 4])
+    v, r = odecode.decode_gaussian_blurred_probs(g['kat_probs'][0], 0, 127, 1.0, 0.1)
+    np.testing.assert_allclose(v, g['kat_values'][0], rtol=0, atol=1e-5)
+    np.testing.assert_array_equal(r, g['kat_rest'][0])
+
+
+def test_decode_random_matches_reference(golden_dir):
+    g = np.load(golden_dir / 'decode_kat.npz')
+    gen = torch.Generator().manual_seed(99)
+    rb = (torch.rand(4, 700, generator=gen) ** 3).numpy()
+    rp = (torch.rand(4, 700, 128, generator=gen) ** 6).numpy()
+    assert abs(rb.astype(np.float64).sum() - float(g['rnd_bounds_checksum'])) < 1e-6
+    assert abs(rp.astype(np.float64).sum() - float(g['rnd_probs_checksum'])) < 1e-4
+    for i in range(4):
+        f2i = odecode.decode_bounds_to_alignment(rb[i])
+        np.testing.assert_array_equal(f2i, g['rnd_frame2item'][i])
+        v, r = odecode.decode_gaussian_blurred_probs(rp[i], 0, 127, 1.0, 0.1)
+        # float32 sums of <= 7 terms in a different association order: a few ulp at |v| <= 127
+        np.testing.assert_allclose(v, g['rnd_values'][i], rtol=0, atol=1e-4)
+        np.testing.assert_array_equal(r, g['rnd_rest'][i])
+        # feed the reference's own values so the segmented decode is compared exactly
+        nm, nd, nk = odecode.decode_note_sequence(g['rnd_frame2item'][i], g['rnd_values'][i], ~g['rnd_rest'][i])
+        np.testing.assert_array_equal(nd, g[f'rnd_note_dur_{i}'])
+        np.testing.assert_array_equal(nk, g[f'rnd_note_mask_{i}'])
+        np.testing.assert_allclose(nm, g[f'rnd_note_midi_{i}'], rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize('cfg_name', ['two_head', 'quant_two_head', 'midi_conformer'])
+def test_plugin_restatement_matches_reference(golden_dir, cfg_name):
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    g = np.load(golden_dir / f'plugin_{cfg_name}.npz')
+    config = synth.named_config(cfg_name)
+    sd = synth.fabricate_state_dict(config, seed=1234)
+    secs = float(g['seconds'])
+    waves = [synth.synth_waveform(int(s), seconds=secs + 0.37 * i) for i, s in enumerate(g['seeds'])]
+    if cfg_name == 'two_head':
+        waves += [synth.edge_case_waveforms()['ragged'], synth.edge_case_waveforms()['short']]
+    quant = cfg_name.startswith('quant')
+    for i, w in enumerate(waves):
+        assert len(w) == int(g[f'clip{i}_num_samples'])
+        out = odecode.infer_clip(sd, config, w, quantized=quant, return_intermediates=True)
+        np.testing.assert_allclose(out['probs'], g[f'clip{i}_probs'], rtol=0, atol=2e-5)
+        np.testing.assert_allclose(out['bounds'], g[f'clip{i}_bounds'], rtol=0, atol=2e-5)
+        # decode restated on the reference's exact probabilities must agree exactly
+        probs, bounds = g[f'clip{i}_probs'], g[f'clip{i}_bounds']
+        f2i = odecode.decode_bounds_to_alignment(bounds)
+        if quant:
+            midi = probs.argmax(-1).astype(np.int64)
+            vals, rest = np.clip(midi, 0, 127), midi == 128
+        else:
+            vals, rest = odecode.decode_gaussian_blurred_probs(probs, 0, 127, 1.0, 0.1)
+        nm, nd, nk = odecode.decode_note_sequence(f2i, vals, ~rest)
+        assert nm.dtype == g[f'clip{i}_note_midi'].dtype == np.float32
+        np.testing.assert_array_equal(nd * (512 / 44100), g[f'clip{i}_note_dur'])
+        np.testing.assert_array_equal(~nk, g[f'clip{i}_note_rest'])
+        np.testing.assert_allclose(nm, g[f'clip{i}_note_midi'], rtol=0, atol=1e-4)
