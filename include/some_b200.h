@@ -1,0 +1,169 @@
+/* some_b200.h — C ABI of libsome_b200.so: the B200 (sm_100a) kernels behind SOME's inference hot path.
+ *
+ * The reference (openvpi/SOME, /root/reference) is pure Python/PyTorch and has NO native FFI; the
+ * "operator interface" of this path is the set of torch calls listed below.  Each entry point names
+ * the reference call site (file:line under /root/reference) it replaces.  INTEGRATION.md shows the
+ * ctypes binding the reference's inference/ package uses to call them.
+ *
+ * Conventions
+ *   - every function returns 0 on success, < 0 on error; some_last_error() returns a thread-local message;
+ *   - all buffers are CALLER-allocated device memory (torch tensors -> data_ptr()); the library never
+ *     allocates, frees or retains them; no torch / ATen types cross this boundary;
+ *   - all work is enqueued on the caller's stream; no hidden synchronisation;
+ *   - "bf16" buffers are raw uint16 bfloat16; row-major; M = total frames of a packed (var-len) batch;
+ *   - cu_frames[B + 1] (int32, device) = prefix sums of per-clip frame counts (clip b = rows
+ *     [cu_frames[b], cu_frames[b + 1])).  Clips never interact: attention, depthwise conv and decode are
+ *     per clip, exactly like the reference's batch-1 loop (inference/base_infer.py:46-53).
+ */
+#ifndef SOME_B200_H_
+#define SOME_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOME_B200_VERSION 100
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+/* Model geometry the kernels are specialised for (all shipped configs: configs/*.yaml). */
+#define SOME_DIM 512
+#define SOME_HEADS 8
+#define SOME_HEAD_DIM 64
+#define SOME_CONV_K 31
+#define SOME_N_MELS 80
+#define SOME_N_FFT 2048
+#define SOME_HOP 512
+#define SOME_MEL_BINS 372 /* spectrum bins 0..371 carry all non-zero mel weights (fmax = 8 kHz) */
+#define SOME_MEL_MAXW 24  /* widest mel filter, in bins */
+
+int some_version(void);
+const char* some_last_error(void);
+
+/* ---- K-mel: modules/rmvpe/spec.py:38-72 (F.pad 1024/1024, torch.stft n_fft 2048 hop 512 periodic Hann,
+ * abs, mel_basis matmul, log(clamp 1e-5)) + the transpose at inference/me_infer.py:31.
+ *   wave          f32, all clips in one buffer (clip starts may be padded for 16-byte alignment)
+ *   clip_start    int64 [B], first sample of each clip in `wave`;  clip_len int64 [B], samples L_b
+ *   cu_frames     int32 [B + 1], T_b = 1 + L_b / 512
+ *   max_frames    max_b T_b (grid sizing: ceil(max_frames / 16) CTAs per clip)
+ *   mel_start     int32 [80]: first spectrum bin with non-zero weight in filter m
+ *   mel_count     int32 [80]: number of contiguous non-zero bins (<= SOME_MEL_MAXW)
+ *   mel_weights   f32 [80][SOME_MEL_MAXW]: those weights (librosa htk / slaney filterbank, spec.py:22-28)
+ *   twiddle       f32 [1024][2]: cos / sin(-2 pi j / 2048), j < 1024 (host-computed in double)
+ *   window        f32 [2048] periodic Hann (torch.hann_window)
+ *   out_f32       f32 [M, 80] or NULL;  out_bf16  bf16 [M, 80] or NULL (A operand of the input projections) */
+int some_mel_logmel(const float* wave, const int64_t* clip_start, const int64_t* clip_len,
+                    const int32_t* cu_frames, int B, int max_frames,
+                    const int32_t* mel_start, const int32_t* mel_count, const float* mel_weights,
+                    const float* twiddle, const float* window, float* out_f32, uint16_t* out_bf16, float clamp,
+                    cudaStream_t stream);
+
+/* ---- K-ln: nn.LayerNorm(512), eps 1e-5 (Gconform.py:57-63 norm1..norm5) over rows of x f32 [M, 512].
+ *   out_bf16: normalised rows as bf16 (A operand of the next GEMM) or NULL
+ *   out_f32 : normalised rows as f32 (the residual stream after norm5) or NULL (may alias x)
+ * groups = 1 or 2 independent problems (midi / bound stream) in one launch. */
+typedef struct {
+  const float* x[2];
+  const float* gamma[2];
+  const float* beta[2];
+  uint16_t* out_bf16[2];
+  float* out_f32[2];
+  int groups;
+  int M;
+} some_ln_args;
+int some_layernorm(const some_ln_args* args, cudaStream_t stream);
+
+/* ---- K-gemm: C = epilogue(A[M,K] . W[N,K]^T), bf16 operands, fp32 accumulation on tcgen05 tensor cores.
+ * Replaces every nn.Linear / 1x1 Conv1d of the trunk (see gemm.cu header for the call sites). */
+enum some_epilogue {
+  SOME_EPI_STORE_BF16 = 0,     /* out bf16 [M,N]   = acc (+ bias)                       to_q|to_kv          */
+  SOME_EPI_SILU_BF16 = 1,      /* out bf16 [M,N]   = silu(acc + bias)                   ffn.ln1 + act       */
+  SOME_EPI_GLU_BF16 = 2,       /* out bf16 [M,N/2] = (a + b_a) * sigmoid(g + b_g)       pointwise_conv1+GLU */
+  SOME_EPI_RESID_F32 = 3,      /* out f32 [M,N]    = alpha * (acc + bias) + resid       ffn.ln2/to_out/pw2  */
+  SOME_EPI_GLU_RESID_F32 = 4,  /* out f32 [M,N/2]  = resid + glu(acc + bias)            Gcf glu1/glu2       */
+  SOME_EPI_BIAS_F32 = 5,       /* out f32 [M,N]    = acc + bias                         inln/inln1, logits  */
+  SOME_EPI_SIGMOID_F32 = 6,    /* out f32 [M,N]    = sigmoid(acc + bias)                outln + sig         */
+  SOME_EPI_SOFTMAX_F32 = 7     /* out f32 [M,N]    = softmax_row(acc + bias), N <= 256  outln + softmax     */
+};
+/* GLU epilogues expect W rows (and bias) packed in 32-row groups: 16 "out" rows followed by their 16
+ * "gate" rows (host packing: some_b200/weights.py).  bias arrays are padded to a multiple of 32 floats. */
+typedef struct {
+  const uint16_t* A[2]; /* bf16 [M, K], row pitch lda */
+  const uint16_t* W[2]; /* bf16 [N, K] */
+  const float* bias[2]; /* f32 [N] or NULL */
+  void* out[2];
+  const float* resid[2];
+  int groups, M, N, K, lda, ld_out, epilogue;
+  float alpha;
+} some_gemm_args;
+int some_gemm(const some_gemm_args* args, cudaStream_t stream);
+
+/* ---- K-attn: F.scaled_dot_product_attention(q, k, v), no mask, scale 64^-0.5, per clip
+ * (base_attention.py:34-45 incl. both rearranges).  qkv bf16 [M, 1536] = [q(8x64) | k(8x64) | v(8x64)]
+ * as written by the fused to_q|to_kv GEMM; out bf16 [M, 512] = 'b h t c -> b t (h c)'. */
+typedef struct {
+  const uint16_t* qkv[2];
+  uint16_t* out[2];
+  int groups;
+  int B;
+  const int32_t* cu_frames; /* device int32 [B + 1] */
+  int max_frames;           /* max_b T_b: grid = ceil(max_frames / 128) query tiles per clip */
+} some_attn_args;
+int some_attention_varlen(const some_attn_args* args, cudaStream_t stream);
+
+/* ---- K-dwconv: depthwise Conv1d(k=31, pad 15, groups=512) + BatchNorm1d(eval) + SiLU
+ * (base_conv.py:66-68) on the packed [M, 512] bf16 layout (no transposes), zero halo per clip.
+ *   w  f32 [31][512] taps with the BN scale folded in;  b f32 [512] = folded bias */
+typedef struct {
+  const uint16_t* x[2];
+  const float* w[2];
+  const float* b[2];
+  uint16_t* out[2]; /* must not alias x (neighbouring tiles read the halo) */
+  int groups;
+  int B;
+  const int32_t* cu_frames; /* device int32 [B + 1] */
+  int max_frames;           /* max_b T_b: grid = ceil(max_frames / 128) tiles per clip (tiles never span clips) */
+} some_dwconv_args;
+int some_dwconv_bn_silu(const some_dwconv_args* args, cudaStream_t stream);
+
+/* ---- K-boundhead: norm5 of the bound stream's last block + cutheard Linear(512,1) + sigmoid
+ * (Gconform.py:63,135,137-138).  x f32 [M,512] -> bounds f32 [M]. */
+int some_bound_head(const float* x, const float* gamma, const float* beta, const float* w, float bias, int M,
+                    float* bounds, cudaStream_t stream);
+
+/* ---- K-decode: utils/infer_utils.py:9-76 + inference/me_infer.py:78-97 (continuous) and
+ * inference/me_quant_infer.py:21-38 (quantized: argmax over 129 bins, rest = bin 128), one CTA per clip.
+ *   probs f32 [M, N] (N = 128 sigmoid bins / 129 softmax bins), bounds f32 [M]
+ *   outputs are packed per clip at offset cu_frames[b] (a clip never has more notes than frames):
+ *     note_midi f32 [M], note_dur i32 [M] (frames; seconds = dur * hop / sr on the host, me_infer.py:95),
+ *     note_rest u8 [M], note_count i32 [B]
+ *   optional debug outputs (may be NULL): frame2item i32 [M], values f32 [M], rest u8 [M]
+ * Integer outputs match the CPU reference exactly for identical inputs: the boundary cumsum is accumulated
+ * sequentially in double and rounded per prefix like ATen's CPU cumsum; per-note sums run in frame order. */
+typedef struct {
+  const float* probs;
+  const float* bounds;
+  const int32_t* cu_frames;
+  int B, M, N;
+  int quantized;
+  float vmin, vmax, deviation, threshold; /* midi_min, midi_max, midi_prob_deviation, rest_threshold */
+  float* note_midi;
+  int32_t* note_dur;
+  uint8_t* note_rest;
+  int32_t* note_count;
+  int32_t* dbg_frame2item;
+  float* dbg_values;
+  uint8_t* dbg_rest;
+  void* scratch; /* device, >= some_decode_scratch_bytes(M) */
+} some_decode_args;
+uint64_t some_decode_scratch_bytes(int M);
+int some_decode_notes(const some_decode_args* args, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOME_B200_H_ */

@@ -1,0 +1,104 @@
+"""ctypes binding of libsome_b200.so (include/some_b200.h).  There is no fallback: if the CUDA
+library is missing or a call fails, this module raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import pathlib
+
+_HERE = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _HERE / 'libsome_b200.so'
+
+EPI_STORE_BF16, EPI_SILU_BF16, EPI_GLU_BF16, EPI_RESID_F32, EPI_GLU_RESID_F32, EPI_BIAS_F32, \
+    EPI_SIGMOID_F32, EPI_SOFTMAX_F32 = range(8)
+
+DIM, HEADS, HEAD_DIM, CONV_K, N_MELS, N_FFT, HOP, MEL_BINS, MEL_MAXW = 512, 8, 64, 31, 80, 2048, 512, 372, 24
+
+_vp = C.c_void_p
+
+
+class LnArgs(C.Structure):
+    _fields_ = [('x', _vp * 2), ('gamma', _vp * 2), ('beta', _vp * 2), ('out_bf16', _vp * 2),
+                ('out_f32', _vp * 2), ('groups', C.c_int), ('M', C.c_int)]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [('A', _vp * 2), ('W', _vp * 2), ('bias', _vp * 2), ('out', _vp * 2), ('resid', _vp * 2),
+                ('groups', C.c_int), ('M', C.c_int), ('N', C.c_int), ('K', C.c_int), ('lda', C.c_int),
+                ('ld_out', C.c_int), ('epilogue', C.c_int), ('alpha', C.c_float)]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [('qkv', _vp * 2), ('out', _vp * 2), ('groups', C.c_int), ('B', C.c_int),
+                ('cu_frames', _vp), ('max_frames', C.c_int)]
+
+
+class DwconvArgs(C.Structure):
+    _fields_ = [('x', _vp * 2), ('w', _vp * 2), ('b', _vp * 2), ('out', _vp * 2), ('groups', C.c_int),
+                ('B', C.c_int), ('cu_frames', _vp), ('max_frames', C.c_int)]
+
+
+class DecodeArgs(C.Structure):
+    _fields_ = [('probs', _vp), ('bounds', _vp), ('cu_frames', _vp), ('B', C.c_int), ('M', C.c_int),
+                ('N', C.c_int), ('quantized', C.c_int), ('vmin', C.c_float), ('vmax', C.c_float),
+                ('deviation', C.c_float), ('threshold', C.c_float), ('note_midi', _vp), ('note_dur', _vp),
+                ('note_rest', _vp), ('note_count', _vp), ('dbg_frame2item', _vp), ('dbg_values', _vp),
+                ('dbg_rest', _vp), ('scratch', _vp)]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    'some_version': (C.c_int, []),
+    'some_last_error': (C.c_char_p, []),
+    'some_mel_logmel': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                  C.c_float, _vp]),
+    'some_layernorm': (C.c_int, [C.POINTER(LnArgs), _vp]),
+    'some_gemm': (C.c_int, [C.POINTER(GemmArgs), _vp]),
+    'some_attention_varlen': (C.c_int, [C.POINTER(AttnArgs), _vp]),
+    'some_dwconv_bn_silu': (C.c_int, [C.POINTER(DwconvArgs), _vp]),
+    'some_bound_head': (C.c_int, [_vp, _vp, _vp, _vp, C.c_float, C.c_int, _vp, _vp]),
+    'some_decode_scratch_bytes': (C.c_uint64, [C.c_int]),
+    'some_decode_notes': (C.c_int, [C.POINTER(DecodeArgs), _vp]),
+}
+
+_lib = None
+
+
+class SomeB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the shared library (once).  Raises if it has not been built: there is no CPU path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.is_file():
+        raise SomeB200Error(
+            f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            f'or `make -C {_HERE / "csrc"}` (nvcc, sm_100a). some_b200 has no CPU fallback.')
+    lib = C.CDLL(os.fspath(LIB_PATH))
+    for name, (restype, argtypes) in EXPORTS.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ''):
+    if rc != 0:
+        msg = load().some_last_error().decode('utf8', 'replace')
+        raise SomeB200Error(f'{what or "libsome_b200"} failed ({rc}): {msg}')
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor, or None."""
+    return None if t is None else t.data_ptr()
+
+
+def pair(a, b=None):
+    arr = (_vp * 2)()
+    arr[0] = ptr(a)
+    arr[1] = ptr(b if b is not None else a)
+    return arr

@@ -1,0 +1,395 @@
+// K-gemm: persistent, warp-specialised bf16 GEMM on the 5th-gen tensor cores (tcgen05) for every dense
+// contraction of the SOME conformer (reference call sites: Gconform.py:29-34 conform_ffn,
+// base_attention.py:31-32,46 to_q/to_kv/to_out, base_conv.py:65,69 pointwise convs, Gconform.py:85-87
+// glu1/glu2, Gconform.py:124-125,135-136 inln/inln1/outln).
+//
+//   C[M, N] = epilogue(A[M, K] . W[N, K]^T)        A, W bf16 row-major (both K-major), fp32 accumulate
+//
+// Roles (384 threads, 1 CTA / SM, grid = #SMs, static round-robin tile schedule, N fastest):
+//   warp 0      TMA producer: A box 128x64 + W box BLOCK_Nx64 (128-B swizzle) into a 4-stage smem ring
+//   warp 1      MMA issuer: one thread, tcgen05.mma cta_group::1 kind::f16, M=128, N=BLOCK_N, K=16 x4 per stage
+//   warp 2      TMEM allocator (512 columns = 2 accumulator stages x 256)
+//   warps 4-11  epilogue: tcgen05.ld 32x32b (thread = one output row), fused bias / SiLU / GLU / residual /
+//               sigmoid / softmax, direct vectorised global stores; overlaps the next tile's mainloop
+//               through the double-buffered accumulator.
+// Up to two independent problems (the "midi" and "bound" streams: same shapes, different weights) run in
+// one launch (groups = 2).
+#include "host_common.h"
+#include "sm100_ptx.cuh"
+
+#include "../../include/some_b200.h"
+
+namespace some {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;
+
+struct GemmGroup {
+  const float* bias;   // [N] in packed-column order, or nullptr
+  void* out;           // bf16 or f32, row pitch ld_out elements
+  const float* resid;  // f32 [M, ld_out] or nullptr (may alias out)
+};
+
+struct GemmParams {
+  int M, N, K;
+  int groups;
+  int ld_out;
+  int n_valid;  // softmax / sigmoid heads: number of real columns
+  float alpha;
+  GemmGroup g[2];
+};
+
+template <int BLOCK_N>
+struct GemmSmem {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Epilogue for one 32-column chunk of one row.  `col` = first packed output column of the chunk.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const GemmGroup& g, int row, bool row_ok, int col,
+                                               const uint32_t (&r)[32]) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  if (g.bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(g.bias + col);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 b = __ldg(b4 + i);
+      v[4 * i + 0] += b.x;
+      v[4 * i + 1] += b.y;
+      v[4 * i + 2] += b.z;
+      v[4 * i + 3] += b.w;
+    }
+  }
+  if constexpr (EPI == SOME_EPI_STORE_BF16 || EPI == SOME_EPI_SILU_BF16) {
+    if constexpr (EPI == SOME_EPI_SILU_BF16) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = silu_fast(v[i]);
+    }
+    if (row_ok) {
+      uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + (size_t)row * p.ld_out + col);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        dst[i] = make_uint4(pack_bf16x2(v[8 * i + 0], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                            pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+    }
+  } else if constexpr (EPI == SOME_EPI_GLU_BF16 || EPI == SOME_EPI_GLU_RESID_F32) {
+    // packed columns: [col, col+16) = "out" channels, [col+16, col+32) = their "gate" channels
+    float o[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = v[i] * sigmoid_fast(v[16 + i]);
+    const int oc = col >> 1;  // output channel of o[0]
+    if (row_ok) {
+      if constexpr (EPI == SOME_EPI_GLU_BF16) {
+        uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + (size_t)row * p.ld_out + oc);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          dst[i] = make_uint4(pack_bf16x2(o[8 * i + 0], o[8 * i + 1]), pack_bf16x2(o[8 * i + 2], o[8 * i + 3]),
+                              pack_bf16x2(o[8 * i + 4], o[8 * i + 5]), pack_bf16x2(o[8 * i + 6], o[8 * i + 7]));
+      } else {
+        const float4* rs = reinterpret_cast<const float4*>(g.resid + (size_t)row * p.ld_out + oc);
+        float4* dst = reinterpret_cast<float4*>(static_cast<float*>(g.out) + (size_t)row * p.ld_out + oc);
+        float4 x[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[i] = rs[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          dst[i] = make_float4(x[i].x + o[4 * i + 0], x[i].y + o[4 * i + 1], x[i].z + o[4 * i + 2],
+                               x[i].w + o[4 * i + 3]);
+      }
+    }
+  } else if constexpr (EPI == SOME_EPI_RESID_F32) {
+    if (row_ok) {
+      const float4* rs = reinterpret_cast<const float4*>(g.resid + (size_t)row * p.ld_out + col);
+      float4* dst = reinterpret_cast<float4*>(static_cast<float*>(g.out) + (size_t)row * p.ld_out + col);
+      float4 x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = rs[i];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        dst[i] = make_float4(fmaf(p.alpha, v[4 * i + 0], x[i].x), fmaf(p.alpha, v[4 * i + 1], x[i].y),
+                             fmaf(p.alpha, v[4 * i + 2], x[i].z), fmaf(p.alpha, v[4 * i + 3], x[i].w));
+    }
+  } else if constexpr (EPI == SOME_EPI_BIAS_F32 || EPI == SOME_EPI_SIGMOID_F32) {
+    if constexpr (EPI == SOME_EPI_SIGMOID_F32) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 1.0f / (1.0f + __expf(-v[i]));
+    }
+    if (row_ok) {
+      float* dst = static_cast<float*>(g.out) + (size_t)row * p.ld_out + col;
+      if (col + 32 <= p.n_valid && (p.ld_out & 3) == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (col + i < p.n_valid) dst[i] = v[i];
+      }
+    }
+  }
+}
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+            const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const GemmParams p) {
+  using S = GemmSmem<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* full_bar = bars;                    // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int tiles_per_group = num_m * num_n;
+  const int num_tiles = tiles_per_group * p.groups;
+  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (p.groups > 1) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmB1);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int grp = tile / tiles_per_group;
+        const int t = tile - grp * tiles_per_group;
+        const int m_blk = t / num_n, n_blk = t - m_blk * num_n;
+        const CUtensorMap* ta = grp == 0 ? &tmA0 : &tmA1;
+        const CUtensorMap* tb = grp == 0 ? &tmB0 : &tmB1;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          uint8_t* sa = smem + stage * S::STAGE_BYTES;
+          tma_load_2d(sa, ta, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          tma_load_2d(sa + S::A_BYTES, tb, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint64_t adesc = umma_desc_kmajor_sw128(sa);
+          const uint64_t bdesc = umma_desc_kmajor_sw128(sa + S::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128-B swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;   // column half of the tile
+    constexpr int COLS_PER_WARP = BLOCK_N / 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int grp = tile / tiles_per_group;
+      const int t = tile - grp * tiles_per_group;
+      const int m_blk = t / num_n, n_blk = t - m_blk * num_n;
+      const GemmGroup& g = p.g[grp];
+      const int row = m_blk * BLOCK_M + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t t_row = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quad * 32) << 16);
+      if constexpr (EPI == SOME_EPI_SOFTMAX_F32) {
+        // whole row in one thread: pass 1 max, pass 2 sum, pass 3 write (TMEM re-reads are cheap)
+        if (half == 0) {
+          uint32_t r[32];
+          float mx = -INFINITY;
+          for (int c = 0; c < p.n_valid; c += 32) {
+            tmem_ld_32x32(t_row + c, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c + i < p.n_valid) mx = fmaxf(mx, __uint_as_float(r[i]) + (g.bias ? __ldg(g.bias + c + i) : 0.f));
+          }
+          float sum = 0.f;
+          for (int c = 0; c < p.n_valid; c += 32) {
+            tmem_ld_32x32(t_row + c, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c + i < p.n_valid) sum += __expf(__uint_as_float(r[i]) + (g.bias ? __ldg(g.bias + c + i) : 0.f) - mx);
+          }
+          const float inv = 1.0f / sum;
+          for (int c = 0; c < p.n_valid; c += 32) {
+            tmem_ld_32x32(t_row + c, r);
+            tmem_ld_wait();
+            if (row_ok) {
+              float* dst = static_cast<float*>(g.out) + (size_t)row * p.ld_out + c;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c + i < p.n_valid)
+                  dst[i] = __expf(__uint_as_float(r[i]) + (g.bias ? __ldg(g.bias + c + i) : 0.f) - mx) * inv;
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < COLS_PER_WARP; c += 32) {
+          const int col_in_tile = half * COLS_PER_WARP + c;
+          const int col = n_blk * BLOCK_N + col_in_tile;
+          if (col >= p.N) break;  // ragged last N tile (heads): nothing to store (warp-uniform)
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + col_in_tile, r);
+          tmem_ld_wait();
+          epilogue_chunk<EPI>(p, g, row, row_ok, col, r);
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int BLOCK_N, int EPI>
+static int launch_gemm(const CUtensorMap* maps, const GemmParams& p, cudaStream_t stream) {
+  using S = GemmSmem<BLOCK_N>;
+  auto kern = gemm_kernel<BLOCK_N, EPI>;
+  static bool configured = false;  // benign race: idempotent attribute set
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    SOME_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(gemm, %d B smem): %s", S::TOTAL, cudaGetErrorString(e));
+    configured = true;
+  }
+  const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int tiles = num_m * num_n * p.groups;
+  int grid = num_sms();
+  if (tiles < grid) grid = tiles;
+  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+  return check_launch("some_gemm");
+}
+
+}  // namespace some
+
+using namespace some;
+
+extern "C" int some_gemm(const some_gemm_args* a, cudaStream_t stream) {
+  SOME_REQUIRE(a != nullptr, "some_gemm: null args");
+  SOME_REQUIRE(a->groups == 1 || a->groups == 2, "some_gemm: groups must be 1 or 2 (got %d)", a->groups);
+  SOME_REQUIRE(a->M >= 0 && a->N > 0 && a->K > 0, "some_gemm: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
+  if (a->M == 0) return 0;
+  SOME_REQUIRE(a->K % 8 == 0, "some_gemm: K must be a multiple of 8 (16-byte TMA pitch), got %d", a->K);
+  const int epi = a->epilogue;
+  const bool head = (epi == SOME_EPI_SOFTMAX_F32 || epi == SOME_EPI_SIGMOID_F32 || epi == SOME_EPI_BIAS_F32);
+  if (!head) SOME_REQUIRE(a->N % 256 == 0, "some_gemm: N must be a multiple of 256 for epilogue %d (got %d)", epi, a->N);
+  if (epi == SOME_EPI_SOFTMAX_F32) SOME_REQUIRE(a->N <= 256, "some_gemm: softmax epilogue needs N <= 256");
+  GemmParams p;
+  p.M = a->M;
+  p.N = a->N;
+  p.K = a->K;
+  p.groups = a->groups;
+  p.ld_out = a->ld_out;
+  p.n_valid = a->N;
+  p.alpha = a->alpha;
+  CUtensorMap maps[4];
+  for (int g = 0; g < 2; ++g) {
+    const int s = g < a->groups ? g : 0;
+    SOME_REQUIRE(a->A[s] != nullptr && a->W[s] != nullptr && a->out[s] != nullptr, "some_gemm: null pointer in group %d", s);
+    if (make_tmap_bf16_2d(&maps[2 * g], a->A[s], a->M, a->K, a->lda, BLOCK_M)) return -1;
+    if (make_tmap_bf16_2d(&maps[2 * g + 1], a->W[s], a->N, a->K, a->K, 256)) return -1;
+    p.g[g].bias = a->bias[s];
+    p.g[g].out = a->out[s];
+    p.g[g].resid = a->resid[s];
+  }
+  const bool needs_resid = (epi == SOME_EPI_RESID_F32 || epi == SOME_EPI_GLU_RESID_F32);
+  if (needs_resid) SOME_REQUIRE(a->resid[0] != nullptr, "some_gemm: epilogue %d needs a residual pointer", epi);
+  switch (epi) {
+    case SOME_EPI_STORE_BF16: return launch_gemm<256, SOME_EPI_STORE_BF16>(maps, p, stream);
+    case SOME_EPI_SILU_BF16: return launch_gemm<256, SOME_EPI_SILU_BF16>(maps, p, stream);
+    case SOME_EPI_GLU_BF16: return launch_gemm<256, SOME_EPI_GLU_BF16>(maps, p, stream);
+    case SOME_EPI_RESID_F32: return launch_gemm<256, SOME_EPI_RESID_F32>(maps, p, stream);
+    case SOME_EPI_GLU_RESID_F32: return launch_gemm<256, SOME_EPI_GLU_RESID_F32>(maps, p, stream);
+    case SOME_EPI_BIAS_F32: return launch_gemm<256, SOME_EPI_BIAS_F32>(maps, p, stream);
+    case SOME_EPI_SIGMOID_F32: return launch_gemm<256, SOME_EPI_SIGMOID_F32>(maps, p, stream);
+    case SOME_EPI_SOFTMAX_F32: return launch_gemm<256, SOME_EPI_SOFTMAX_F32>(maps, p, stream);
+    default: SOME_REQUIRE(false, "some_gemm: unknown epilogue %d", epi);
+  }
+  return -1;
+}

@@ -1,0 +1,230 @@
+// Row-wise HBM-bound kernels of the conformer trunk on the packed [M, 512] layout:
+//   K-ln        nn.LayerNorm(512, eps 1e-5)                       Gconform.py:57-63 (norm1..norm5)
+//   K-boundhead norm5 + cutheard Linear(512, 1) + sigmoid         Gconform.py:63,135,137-138
+//   K-dwconv    depthwise Conv1d(k=31, pad 15) + BatchNorm1d(eval) + SiLU, per-clip zero halo
+//                                                                 base_conv.py:66-68
+// Roofline: HBM.  LN reads 2 KB and writes 1-3 KB per row; dwconv reads/writes 1 KB + 1 KB per row.
+#include "host_common.h"
+#include "sm100_ptx.cuh"
+
+#include "../../include/some_b200.h"
+
+namespace some {
+
+constexpr int D = SOME_DIM;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct LnParams {
+  const float* x[2];
+  const float* gamma[2];
+  const float* beta[2];
+  __nv_bfloat16* out_bf16[2];
+  float* out_f32[2];
+  int M;
+};
+
+// one warp per row: lane holds columns {128 i + 4 lane .. +3}, i < 4 (coalesced float4)
+__device__ __forceinline__ void ln_row(const float* __restrict__ xr, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, int lane, float (&y)[16]) {
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float4 t = *reinterpret_cast<const float4*>(xr + 128 * i + 4 * lane);
+    v[4 * i] = t.x, v[4 * i + 1] = t.y, v[4 * i + 2] = t.z, v[4 * i + 3] = t.w;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float d = v[i] - mean;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + 128 * i + 4 * lane));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + 128 * i + 4 * lane));
+    y[4 * i + 0] = fmaf((v[4 * i + 0] - mean) * rstd, g.x, b.x);
+    y[4 * i + 1] = fmaf((v[4 * i + 1] - mean) * rstd, g.y, b.y);
+    y[4 * i + 2] = fmaf((v[4 * i + 2] - mean) * rstd, g.z, b.z);
+    y[4 * i + 3] = fmaf((v[4 * i + 3] - mean) * rstd, g.w, b.w);
+  }
+}
+
+__global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
+  const int grp = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= p.M) return;
+  float y[16];
+  ln_row(p.x[grp] + (size_t)row * D, p.gamma[grp], p.beta[grp], lane, y);
+  if (p.out_f32[grp] != nullptr) {
+    float* o = p.out_f32[grp] + (size_t)row * D;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4*>(o + 128 * i + 4 * lane) = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+  }
+  if (p.out_bf16[grp] != nullptr) {
+    __nv_bfloat16* o = p.out_bf16[grp] + (size_t)row * D;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<uint2*>(o + 128 * i + 4 * lane) =
+          make_uint2(pack_bf16x2(y[4 * i], y[4 * i + 1]), pack_bf16x2(y[4 * i + 2], y[4 * i + 3]));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bound_head_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  const float* __restrict__ w, float bias, int M, float* __restrict__ bounds) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  float y[16];
+  ln_row(x + (size_t)row * D, gamma, beta, lane, y);
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 ww = __ldg(reinterpret_cast<const float4*>(w + 128 * i + 4 * lane));
+    dot = fmaf(y[4 * i], ww.x, dot);
+    dot = fmaf(y[4 * i + 1], ww.y, dot);
+    dot = fmaf(y[4 * i + 2], ww.z, dot);
+    dot = fmaf(y[4 * i + 3], ww.w, dot);
+  }
+  dot = warp_sum(dot) + bias;
+  if (lane == 0) bounds[row] = 1.0f / (1.0f + expf(-dot));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Depthwise conv.  CTA = one 128-frame tile of one clip x 64 channels (grid.x = clip * tiles_per_clip + tile;
+// tiles past the end of a short clip exit at once).  The (128 + 30) x 64 input
+// window is staged in shared memory (zeros outside the clip).  Each thread owns a channel pair and 16
+// consecutive frames: 31 x 2 folded taps and 16 x 2 accumulators live in registers, the 46 input rows
+// stream through once (row-major accumulation, fully unrolled, no per-tap predicates).
+constexpr int DW_T = 128;     // frames per tile
+constexpr int DW_C = 64;      // channels per CTA
+constexpr int DW_FR = 16;     // frames per thread
+constexpr int DW_HALO = 15;
+
+struct DwParams {
+  const __nv_bfloat16* x[2];
+  const float* w[2];  // [31][512]
+  const float* b[2];  // [512]
+  __nv_bfloat16* out[2];
+  const int32_t* cu_frames;
+  int tiles_per_clip;
+};
+
+__global__ void __launch_bounds__(256) dwconv_kernel(const DwParams p) {
+  __shared__ __align__(16) __nv_bfloat16 tile[(DW_T + 2 * DW_HALO) * DW_C];
+  const int grp = blockIdx.z;
+  const int c0 = blockIdx.y * DW_C;
+  const int clip = blockIdx.x / p.tiles_per_clip;
+  const int tile_in_clip = blockIdx.x - clip * p.tiles_per_clip;
+  const int clip_begin = p.cu_frames[clip], clip_end = p.cu_frames[clip + 1];
+  const int row0 = clip_begin + tile_in_clip * DW_T;
+  if (row0 >= clip_end) return;
+  const __nv_bfloat16* __restrict__ x = p.x[grp];
+
+  // stage rows [row0 - 15, row0 + 128 + 15) x 64 channels: 8 x 16-byte chunks per row
+  for (int i = threadIdx.x; i < (DW_T + 2 * DW_HALO) * 8; i += 256) {
+    const int r = i >> 3, ch = i & 7;
+    const int grow = row0 - DW_HALO + r;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (grow >= clip_begin && grow < clip_end)
+      v = *reinterpret_cast<const uint4*>(x + (size_t)grow * D + c0 + ch * 8);
+    *reinterpret_cast<uint4*>(tile + r * DW_C + ch * 8) = v;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = c0 + 2 * lane;
+  float w0[SOME_CONV_K], w1[SOME_CONV_K];
+#pragma unroll
+  for (int k = 0; k < SOME_CONV_K; ++k) {
+    const float2 ww = __ldg(reinterpret_cast<const float2*>(p.w[grp] + k * D + c));
+    w0[k] = ww.x, w1[k] = ww.y;
+  }
+  const float2 bb = __ldg(reinterpret_cast<const float2*>(p.b[grp] + c));
+  float a0[DW_FR], a1[DW_FR];
+#pragma unroll
+  for (int f = 0; f < DW_FR; ++f) a0[f] = bb.x, a1[f] = bb.y;
+  __syncthreads();
+  const int f0 = warp * DW_FR;  // first output frame (tile-relative) of this thread
+#pragma unroll
+  for (int r = 0; r < DW_FR + SOME_CONV_K - 1; ++r) {
+    const __nv_bfloat162 xv = *reinterpret_cast<const __nv_bfloat162*>(tile + (f0 + r) * DW_C + 2 * lane);
+    const float x0 = __low2float(xv), x1 = __high2float(xv);
+#pragma unroll
+    for (int f = 0; f < DW_FR; ++f) {
+      const int k = r - f;  // tap index: output f reads input rows f .. f + 30 (tile row = frame + 15 - 15 + k)
+      if (k >= 0 && k < SOME_CONV_K) {
+        a0[f] = fmaf(w0[k], x0, a0[f]);
+        a1[f] = fmaf(w1[k], x1, a1[f]);
+      }
+    }
+  }
+  __nv_bfloat16* __restrict__ out = p.out[grp];
+#pragma unroll
+  for (int f = 0; f < DW_FR; ++f) {
+    const int grow = row0 + f0 + f;
+    if (grow < clip_end)
+      *reinterpret_cast<uint32_t*>(out + (size_t)grow * D + c) = pack_bf16x2(silu_fast(a0[f]), silu_fast(a1[f]));
+  }
+}
+
+}  // namespace some
+
+using namespace some;
+
+extern "C" int some_layernorm(const some_ln_args* a, cudaStream_t stream) {
+  SOME_REQUIRE(a != nullptr && (a->groups == 1 || a->groups == 2), "some_layernorm: bad args");
+  if (a->M <= 0) return 0;
+  LnParams p;
+  for (int g = 0; g < 2; ++g) {
+    const int s = g < a->groups ? g : 0;
+    SOME_REQUIRE(a->x[s] && a->gamma[s] && a->beta[s], "some_layernorm: null input in group %d", s);
+    SOME_REQUIRE(a->out_bf16[s] || a->out_f32[s], "some_layernorm: no output in group %d", s);
+    p.x[g] = a->x[s], p.gamma[g] = a->gamma[s], p.beta[g] = a->beta[s];
+    p.out_bf16[g] = reinterpret_cast<__nv_bfloat16*>(a->out_bf16[s]);
+    p.out_f32[g] = a->out_f32[s];
+  }
+  p.M = a->M;
+  dim3 grid((a->M + 7) / 8, a->groups);
+  layernorm_kernel<<<grid, 256, 0, stream>>>(p);
+  return check_launch("some_layernorm");
+}
+
+extern "C" int some_bound_head(const float* x, const float* gamma, const float* beta, const float* w, float bias,
+                               int M, float* bounds, cudaStream_t stream) {
+  SOME_REQUIRE(x && gamma && beta && w && bounds, "some_bound_head: null pointer");
+  if (M <= 0) return 0;
+  bound_head_kernel<<<(M + 7) / 8, 256, 0, stream>>>(x, gamma, beta, w, bias, M, bounds);
+  return check_launch("some_bound_head");
+}
+
+extern "C" int some_dwconv_bn_silu(const some_dwconv_args* a, cudaStream_t stream) {
+  SOME_REQUIRE(a != nullptr && (a->groups == 1 || a->groups == 2), "some_dwconv_bn_silu: bad args");
+  if (a->B <= 0 || a->max_frames <= 0) return 0;
+  SOME_REQUIRE(a->cu_frames != nullptr, "some_dwconv_bn_silu: null cu_frames");
+  DwParams p;
+  for (int g = 0; g < 2; ++g) {
+    const int s = g < a->groups ? g : 0;
+    SOME_REQUIRE(a->x[s] && a->w[s] && a->b[s] && a->out[s], "some_dwconv_bn_silu: null pointer in group %d", s);
+    p.x[g] = reinterpret_cast<const __nv_bfloat16*>(a->x[s]);
+    p.w[g] = a->w[s], p.b[g] = a->b[s];
+    p.out[g] = reinterpret_cast<__nv_bfloat16*>(a->out[s]);
+  }
+  p.cu_frames = a->cu_frames;
+  p.tiles_per_clip = (a->max_frames + DW_T - 1) / DW_T;
+  const long long gx = 1ll * p.tiles_per_clip * a->B;
+  SOME_REQUIRE(gx < (1ll << 31), "some_dwconv_bn_silu: grid too large");
+  dim3 grid(static_cast<unsigned>(gx), D / DW_C, a->groups);
+  dwconv_kernel<<<grid, 256, 0, stream>>>(p);
+  return check_launch("some_dwconv_bn_silu");
+}

@@ -1,0 +1,266 @@
+"""Batched SOME inference engine: packs clips var-len, launches the sm_100a kernels of
+libsome_b200.so in order on the current CUDA stream and unpacks the decoded notes.
+
+Equivalent to running the reference's batch-1 loop (inference/base_infer.py:46-53) once per clip:
+clips never interact (per-clip attention, per-clip zero-padded depthwise conv, per-clip decode).
+Launch sequence per conform_blocke (Gconform.py:56-63), both streams (midi / bound) in every launch:
+    LN1 -> GEMM(ffn1.ln1)+SiLU -> GEMM(ffn1.ln2)*0.5+x -> LN2 -> GEMM(to_q|to_kv) -> attention ->
+    GEMM(to_out)+x -> LN3 -> GEMM(pointwise_conv1)+GLU -> dwconv+BN+SiLU -> GEMM(pointwise_conv2)+x ->
+    LN4 -> GEMM(ffn2.ln1)+SiLU -> GEMM(ffn2.ln2)*0.5+x -> LN5
+The residual stream x is fp32 [M, 512]; GEMM operands are bf16; accumulation is fp32.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import DIM, FFN_DIM, check_supported
+from .weights import ModelWeights, mel_tables
+
+HOP = 512
+
+
+def frames_of(num_samples: int) -> int:
+    return 1 + num_samples // HOP
+
+
+class _Workspace:
+    def __init__(self, m: int, outdim: int, device):
+        bf, f32 = torch.bfloat16, torch.float32
+        self.m = m
+        self.x = torch.empty((2, m, DIM), dtype=f32, device=device)          # residual streams
+        self.a = torch.empty((2, m, DIM), dtype=bf, device=device)           # LN out / attention out / dwconv out
+        self.h = torch.empty((2, m, FFN_DIM), dtype=bf, device=device)       # FFN hidden
+        self.qkv = torch.empty((2, m, 3 * DIM), dtype=bf, device=device)
+        self.g = torch.empty((2, m, DIM), dtype=bf, device=device)           # GLU out (dwconv in)
+        self.units = torch.empty((m, 80), dtype=bf, device=device)
+        self.probs = torch.empty((m, outdim), dtype=f32, device=device)
+        self.bounds = torch.empty((m,), dtype=f32, device=device)
+        self.note_midi = torch.empty((m,), dtype=f32, device=device)
+        self.note_dur = torch.empty((m,), dtype=torch.int32, device=device)
+        self.note_rest = torch.empty((m,), dtype=torch.uint8, device=device)
+        self.scratch = torch.empty((int(_lib.load().some_decode_scratch_bytes(m)),), dtype=torch.uint8, device=device)
+
+
+class Engine:
+    def __init__(self, config: dict, state_dict, device='cuda'):
+        self.lib = _lib.load()
+        check_supported(config)
+        self.config = config
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise _lib.SomeB200Error('some_b200 runs on CUDA devices only (sm_100a); there is no CPU path')
+        self.quantized = False
+        self.w = ModelWeights(state_dict, config, self.device)
+        self.mel = mel_tables(config, self.device)
+        self.outdim = config['midi_num_bins']
+        self.timestep = config['hop_size'] / config['audio_sample_rate']
+        self._ws: Optional[_Workspace] = None
+        self.launches = 0
+
+    # ------------------------------------------------------------------ helpers
+    @property
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def workspace(self, m: int) -> _Workspace:
+        if self._ws is None or self._ws.m < m:
+            self._ws = None
+            self._ws = _Workspace(max(m, 1), self.outdim, self.device)
+        return self._ws
+
+    def _gemm(self, a0, a1, w0, w1, b0, b1, out0, out1, r0, r1, m, n, k, lda, ld_out, epi, alpha=1.0, groups=2):
+        g = _lib.GemmArgs()
+        g.A, g.W = _lib.pair(a0, a1), _lib.pair(w0, w1)
+        g.bias, g.out, g.resid = _lib.pair(b0, b1), _lib.pair(out0, out1), _lib.pair(r0, r1)
+        g.groups, g.M, g.N, g.K, g.lda, g.ld_out, g.epilogue, g.alpha = groups, m, n, k, lda, ld_out, epi, alpha
+        _lib.check(self.lib.some_gemm(C.byref(g), self._stream), 'some_gemm')
+        self.launches += 1
+
+    def _ln(self, x, gamma, beta, out_bf16, out_f32, m):
+        a = _lib.LnArgs()
+        a.x = _lib.pair(x[0], x[1])
+        a.gamma, a.beta = _lib.pair(*gamma), _lib.pair(*beta)
+        a.out_bf16 = _lib.pair(out_bf16[0], out_bf16[1]) if out_bf16 is not None else (C.c_void_p * 2)()
+        a.out_f32 = _lib.pair(out_f32[0], out_f32[1]) if out_f32 is not None else (C.c_void_p * 2)()
+        a.groups, a.M = 2, m
+        _lib.check(self.lib.some_layernorm(C.byref(a), self._stream), 'some_layernorm')
+        self.launches += 1
+
+    # ------------------------------------------------------------------ stages
+    def run_mel(self, wave: torch.Tensor, clip_start: torch.Tensor, clip_len: torch.Tensor, cu_frames: torch.Tensor,
+                b: int, max_frames: int, out_f32: Optional[torch.Tensor], out_bf16: Optional[torch.Tensor]):
+        """K-mel (spec.py:38-72).  wave f32; clip i = wave[start_i : start_i + len_i]; outputs [M, 80]."""
+        t = self.mel
+        _lib.check(self.lib.some_mel_logmel(
+            wave.data_ptr(), clip_start.data_ptr(), clip_len.data_ptr(), cu_frames.data_ptr(), b, max_frames,
+            t['mel_start'].data_ptr(), t['mel_count'].data_ptr(), t['mel_weights'].data_ptr(),
+            t['twiddle'].data_ptr(), t['window'].data_ptr(), _lib.ptr(out_f32), _lib.ptr(out_bf16),
+            1e-5, self._stream), 'some_mel_logmel')
+        self.launches += 1
+
+    def _block(self, ws: _Workspace, blk, m: int, b: int, cu_frames, max_frames: int, last: bool):
+        x, a, h, qkv, g = ws.x, ws.a, ws.h, ws.qkv, ws.g
+        lib, st = self.lib, self._stream
+        w0, w1 = blk
+
+        def ln(i, out_bf16=a, out_f32=None):
+            self._ln(x, (w0.ln_g[i], w1.ln_g[i]), (w0.ln_b[i], w1.ln_b[i]), out_bf16, out_f32, m)
+
+        def ffn(i):
+            f0, f1 = w0.ffn[i], w1.ffn[i]
+            self._gemm(a[0], a[1], f0['w1'], f1['w1'], f0['b1'], f1['b1'], h[0], h[1], None, None,
+                       m, FFN_DIM, DIM, DIM, FFN_DIM, _lib.EPI_SILU_BF16)
+            self._gemm(h[0], h[1], f0['w2'], f1['w2'], f0['b2'], f1['b2'], x[0], x[1], x[0], x[1],
+                       m, DIM, FFN_DIM, FFN_DIM, DIM, _lib.EPI_RESID_F32, alpha=0.5)
+
+        ln(0)
+        ffn(0)                                                                   # Gconform.py:57
+        ln(1)
+        self._gemm(a[0], a[1], w0.w_qkv, w1.w_qkv, None, None, qkv[0], qkv[1], None, None,
+                   m, 3 * DIM, DIM, DIM, 3 * DIM, _lib.EPI_STORE_BF16)
+        at = _lib.AttnArgs()
+        at.qkv, at.out = _lib.pair(qkv[0], qkv[1]), _lib.pair(a[0], a[1])
+        at.groups, at.B, at.cu_frames, at.max_frames = 2, b, cu_frames.data_ptr(), max_frames
+        _lib.check(lib.some_attention_varlen(C.byref(at), st), 'some_attention_varlen')
+        self.launches += 1
+        self._gemm(a[0], a[1], w0.w_out, w1.w_out, w0.b_out, w1.b_out, x[0], x[1], x[0], x[1],
+                   m, DIM, DIM, DIM, DIM, _lib.EPI_RESID_F32)                   # :60
+        ln(2)
+        self._gemm(a[0], a[1], w0.w_pw1, w1.w_pw1, w0.b_pw1, w1.b_pw1, g[0], g[1], None, None,
+                   m, 2 * DIM, DIM, DIM, DIM, _lib.EPI_GLU_BF16)                # base_conv.py:65
+        dw = _lib.DwconvArgs()
+        dw.x, dw.w, dw.b = _lib.pair(g[0], g[1]), _lib.pair(w0.w_dw, w1.w_dw), _lib.pair(w0.b_dw, w1.b_dw)
+        dw.out = _lib.pair(a[0], a[1])
+        dw.groups, dw.B, dw.cu_frames, dw.max_frames = 2, b, cu_frames.data_ptr(), max_frames
+        _lib.check(lib.some_dwconv_bn_silu(C.byref(dw), st), 'some_dwconv_bn_silu')   # base_conv.py:66-68
+        self.launches += 1
+        self._gemm(a[0], a[1], w0.w_pw2, w1.w_pw2, w0.b_pw2, w1.b_pw2, x[0], x[1], x[0], x[1],
+                   m, DIM, DIM, DIM, DIM, _lib.EPI_RESID_F32)                   # base_conv.py:69 + Gconform.py:61
+        ln(3)
+        ffn(1)                                                                   # :62
+        if not last:
+            ln(4, out_bf16=a, out_f32=x)                                         # :63 (residual for the next Gcf)
+        else:
+            # final pair: midi stream -> normalised bf16 for outln; bound stream -> fused norm5 + cutheard + sigmoid
+            al = _lib.LnArgs()
+            al.x, al.gamma, al.beta = _lib.pair(x[0]), _lib.pair(w0.ln_g[4]), _lib.pair(w0.ln_b[4])
+            al.out_bf16, al.out_f32 = _lib.pair(a[0]), (C.c_void_p * 2)()
+            al.groups, al.M = 1, m
+            _lib.check(lib.some_layernorm(C.byref(al), st), 'some_layernorm')
+            _lib.check(lib.some_bound_head(x[1].data_ptr(), w1.ln_g[4].data_ptr(), w1.ln_b[4].data_ptr(),
+                                           self.w.w_cut.data_ptr(), self.w.b_cut, m, ws.bounds.data_ptr(), st),
+                       'some_bound_head')
+            self.launches += 2
+
+    def run_trunk(self, ws: _Workspace, m: int, b: int, cu_frames: torch.Tensor, max_frames: int,
+                  head: str = 'sigmoid', taps: Optional[dict] = None):
+        """Gmidi_conform.forward (Gconform.py:119-140) + the head activation of midi_conforms.forward
+        (Gmidi_conform.py:30-40).  Reads ws.units; writes ws.probs [m, outdim] and ws.bounds [m].
+        head: 'sigmoid' | 'softmax' | 'logits'."""
+        w, x, a = self.w, ws.x, ws.a
+        self._gemm(ws.units, ws.units, w.w_in[0], w.w_in[1], w.b_in[0], w.b_in[1], x[0], x[1], None, None,
+                   m, DIM, 80, 80, DIM, _lib.EPI_BIAS_F32)                       # inln / inln1
+        for i in range(w.lay):
+            self._block(ws, w.blocks[i], m, b, cu_frames, max_frames, last=False)
+            # Gcf.forward :85-87: midi += GLU(glu2(bound)); bound += GLU(glu1(midi))  (a = bf16 copies of norm5 out)
+            self._gemm(a[1], a[0], w.glu_w[i][1], w.glu_w[i][0], w.glu_b[i][1], w.glu_b[i][0],
+                       x[0], x[1], x[0], x[1], m, 2 * DIM, DIM, DIM, DIM, _lib.EPI_GLU_RESID_F32)
+            if taps is not None:
+                taps[f'model.cf_lay.{i}:midi'] = x[0, :m].clone()
+                taps[f'model.cf_lay.{i}:bound'] = x[1, :m].clone()
+        self._block(ws, w.blocks[w.lay], m, b, cu_frames, max_frames, last=True)
+        epi = {'sigmoid': _lib.EPI_SIGMOID_F32, 'softmax': _lib.EPI_SOFTMAX_F32, 'logits': _lib.EPI_BIAS_F32}[head]
+        self._gemm(a[0], None, w.w_head, None, w.b_head, None, ws.probs, None, None, None,
+                   m, self.outdim, DIM, DIM, self.outdim, epi, groups=1)          # outln (+ sigmoid / softmax)
+
+    def run_decode(self, ws: _Workspace, m: int, b: int, cu_frames: torch.Tensor, note_count: torch.Tensor,
+                   quantized: bool, dbg: Optional[dict] = None, probs=None, bounds=None):
+        cfg = self.config
+        d = _lib.DecodeArgs()
+        d.probs = (probs if probs is not None else ws.probs).data_ptr()
+        d.bounds = (bounds if bounds is not None else ws.bounds).data_ptr()
+        d.cu_frames = cu_frames.data_ptr()
+        d.B, d.M, d.N, d.quantized = b, m, self.outdim, int(quantized)
+        d.vmin, d.vmax = float(cfg['midi_min']), float(cfg['midi_max'])
+        d.deviation = float(cfg.get('midi_prob_deviation', 1.0))
+        d.threshold = float(cfg.get('rest_threshold', 0.1))
+        d.note_midi, d.note_dur, d.note_rest = ws.note_midi.data_ptr(), ws.note_dur.data_ptr(), ws.note_rest.data_ptr()
+        d.note_count = note_count.data_ptr()
+        if dbg is not None:
+            dbg['frame2item'] = torch.zeros(m, dtype=torch.int32, device=self.device)
+            dbg['values'] = torch.zeros(m, dtype=torch.float32, device=self.device)
+            dbg['rest'] = torch.zeros(m, dtype=torch.uint8, device=self.device)
+            d.dbg_frame2item, d.dbg_values, d.dbg_rest = (dbg[k].data_ptr() for k in ('frame2item', 'values', 'rest'))
+        d.scratch = ws.scratch.data_ptr()
+        _lib.check(self.lib.some_decode_notes(C.byref(d), self._stream), 'some_decode_notes')
+        self.launches += 1
+
+    # ------------------------------------------------------------------ public batched entry point
+    def pack(self, waveforms: Sequence[np.ndarray]):
+        """Concatenates clips into one pinned host buffer (each clip start 16-byte aligned) and builds the
+        var-len tables [starts | lens] (int64) and cu_frames (int32).  Host only."""
+        b = len(waveforms)
+        lens = np.array([int(w.shape[0]) for w in waveforms], dtype=np.int64)
+        padded = (lens + 3) & ~3
+        starts = np.zeros(b, dtype=np.int64)
+        np.cumsum(padded[:-1], out=starts[1:])
+        total = int(padded.sum())
+        host = torch.empty(max(total, 4), dtype=torch.float32).pin_memory()
+        hv = host.numpy()
+        for s, w, n, pn in zip(starts, waveforms, lens, padded):
+            hv[s:s + n] = w
+            hv[s + n:s + pn] = 0.0
+        cu = np.zeros(b + 1, dtype=np.int32)
+        np.cumsum(1 + lens // HOP, out=cu[1:])                  # T = 1 + L // hop (spec.py:48-60)
+        tables = torch.from_numpy(np.concatenate([starts, lens])).pin_memory()
+        return host, tables, cu
+
+    def infer(self, waveforms: Sequence[np.ndarray], quantized: bool = False,
+              return_intermediates: bool = False) -> List[Dict[str, np.ndarray]]:
+        """waveform-in -> notes-out for a list of clips: the batched equivalent of BaseInference.infer
+        (base_infer.py:46-53).  One H2D copy of the audio, one packed D2H of the notes."""
+        b = len(waveforms)
+        if b == 0:
+            return []
+        host, tables, cu = self.pack(waveforms)
+        m, max_frames = int(cu[-1]), int(np.diff(cu).max())
+        dev = self.device
+        with torch.cuda.device(dev):
+            wave = host.to(dev, non_blocking=True)
+            tables_d = tables.to(dev, non_blocking=True)
+            cu_d = torch.from_numpy(cu).pin_memory().to(dev, non_blocking=True)
+            ws = self.workspace(m)
+            note_count = torch.empty(b, dtype=torch.int32, device=dev)
+            mel_f32 = torch.empty((m, 80), dtype=torch.float32, device=dev) if return_intermediates else None
+            self.run_mel(wave, tables_d[:b], tables_d[b:], cu_d, b, max_frames, mel_f32, ws.units)
+            self.run_trunk(ws, m, b, cu_d, max_frames, 'softmax' if quantized else 'sigmoid')
+            self.run_decode(ws, m, b, cu_d, note_count, quantized)
+            nm = ws.note_midi[:m].to('cpu', non_blocking=True)
+            nd = ws.note_dur[:m].to('cpu', non_blocking=True)
+            nr = ws.note_rest[:m].to('cpu', non_blocking=True)
+            nc = note_count.to('cpu', non_blocking=True)
+            extra = None
+            if return_intermediates:
+                extra = (mel_f32.cpu(), ws.probs[:m].cpu(), ws.bounds[:m].cpu())
+            torch.cuda.current_stream(dev).synchronize()
+        return self.unpack(cu, nc.numpy(), nm.numpy(), nd.numpy(), nr.numpy(), extra)
+
+    def unpack(self, cu, nc, nm, nd, nr, extra=None) -> List[Dict[str, np.ndarray]]:
+        out = []
+        for i in range(len(cu) - 1):
+            r0, n = int(cu[i]), int(nc[i])
+            item = {
+                'note_midi': nm[r0:r0 + n].copy(),
+                'note_dur': nd[r0:r0 + n].astype(np.int64) * self.timestep,     # me_infer.py:95 (int64 * float)
+                'note_rest': nr[r0:r0 + n].astype(bool),
+            }
+            if extra is not None:
+                r1 = int(cu[i + 1])
+                item.update(mel=extra[0][r0:r1].numpy(), probs=extra[1][r0:r1].numpy(), bounds=extra[2][r0:r1].numpy())
+            out.append(item)
+        return out

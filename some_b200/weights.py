@@ -1,0 +1,144 @@
+"""Host-side packing of a reference checkpoint (``state_dict`` of
+``modules.model.Gmidi_conform.midi_conforms``) into the device layouts the sm_100a kernels consume:
+
+* every nn.Linear / 1x1 Conv1d weight -> bf16 [N, K] (K-major, exactly nn.Linear's own layout);
+* to_q | to_kv concatenated to one [1536, 512] matrix (base_attention.py:31-32: q, then k, then v);
+* GLU producers (pointwise_conv1, glu1, glu2) row-interleaved in groups of 16 so an output channel
+  and its gate land in the same 32-column chunk of the GEMM epilogue;
+* BatchNorm1d (eval, eps 1e-5) folded into the depthwise taps: w' = w * g / sqrt(var + eps),
+  b' = (b - mean) * g / sqrt(var + eps) + beta  (base_conv.py:66-67);
+* mel filterbank (librosa htk / slaney, spec.py:22-28) as per-filter contiguous bin ranges, periodic
+  Hann window and double-precision FFT twiddles.
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import DIM
+
+BN_EPS = 1e-5
+
+
+# --------------------------------------------------------------------------- mel front-end tables
+def mel_filterbank_htk_slaney(sr: int, n_fft: int, n_mels: int, fmin: float, fmax: float) -> np.ndarray:
+    """librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax, htk=True) with the default Slaney area
+    normalisation (librosa 0.9.x), as called at modules/rmvpe/spec.py:22-28.  float32 [n_mels, 1 + n_fft/2]."""
+    if fmax is None:
+        fmax = sr / 2.0
+    n_bins = 1 + n_fft // 2
+    fft_freqs = np.linspace(0.0, sr / 2.0, n_bins)
+    to_mel = lambda f: 2595.0 * np.log10(1.0 + f / 700.0)
+    edges_mel = np.linspace(to_mel(float(fmin)), to_mel(float(fmax)), n_mels + 2)
+    edges_hz = 700.0 * (10.0 ** (edges_mel / 2595.0) - 1.0)
+    width = np.diff(edges_hz)
+    bank = np.zeros((n_mels, n_bins), dtype=np.float32)
+    for m in range(n_mels):
+        rising = (fft_freqs - edges_hz[m]) / width[m]
+        falling = (edges_hz[m + 2] - fft_freqs) / width[m + 1]
+        bank[m] = np.maximum(0.0, np.minimum(rising, falling))
+    bank *= (2.0 / (edges_hz[2:] - edges_hz[:-2]))[:, None]
+    return bank
+
+
+def mel_tables(config: dict, device) -> Dict[str, torch.Tensor]:
+    sr, n_fft = config['audio_sample_rate'], config['win_size']
+    bank = mel_filterbank_htk_slaney(sr, n_fft, config['units_dim'], config['fmin'], config['fmax'])
+    nz = bank != 0
+    start = np.zeros(bank.shape[0], dtype=np.int32)
+    count = np.zeros(bank.shape[0], dtype=np.int32)
+    weights = np.zeros((bank.shape[0], _lib.MEL_MAXW), dtype=np.float32)
+    for m in range(bank.shape[0]):
+        idx = np.nonzero(nz[m])[0]
+        if idx.size == 0:
+            continue
+        lo, hi = int(idx[0]), int(idx[-1])
+        if hi >= _lib.MEL_BINS or hi - lo + 1 > _lib.MEL_MAXW:
+            raise NotImplementedError(
+                f'mel filter {m} spans bins {lo}..{hi}: outside what the fused kernel keeps '
+                f'({_lib.MEL_BINS} bins, {_lib.MEL_MAXW} per filter); fmin/fmax/sr differ from the shipped configs')
+        start[m], count[m] = lo, hi - lo + 1
+        weights[m, :hi - lo + 1] = bank[m, lo:hi + 1]
+    j = np.arange(1024, dtype=np.float64)
+    tw = np.stack([np.cos(-2.0 * np.pi * j / 2048.0), np.sin(-2.0 * np.pi * j / 2048.0)], axis=1).astype(np.float32)
+    n = np.arange(n_fft, dtype=np.float64)
+    window = torch.hann_window(n_fft, periodic=True, dtype=torch.float32)    # spec.py:45 torch.hann_window
+    return {
+        'mel_start': torch.from_numpy(start).to(device),
+        'mel_count': torch.from_numpy(count).to(device),
+        'mel_weights': torch.from_numpy(weights).to(device),
+        'twiddle': torch.from_numpy(tw).to(device),
+        'window': window.to(device),
+        'bank': bank,
+    }
+
+
+# --------------------------------------------------------------------------- trunk weights
+def glu_pack_rows(w: torch.Tensor) -> torch.Tensor:
+    """[2C, ...] (rows 0..C-1 = out, C..2C-1 = gate) -> groups of 32 rows: 16 out rows then their 16 gates."""
+    c = w.shape[0] // 2
+    assert c % 16 == 0
+    out = w[:c].reshape(c // 16, 16, *w.shape[1:])
+    gate = w[c:].reshape(c // 16, 16, *w.shape[1:])
+    return torch.cat([out, gate], dim=1).reshape(w.shape)
+
+
+def _pad32(v: torch.Tensor) -> torch.Tensor:
+    n = v.shape[0]
+    pad = (-n) % 32
+    return torch.cat([v, v.new_zeros(pad)]) if pad else v
+
+
+class BlockWeights:
+    """Device tensors of one conform_blocke (Gconform.py:37-63)."""
+
+    def __init__(self, sd, p: str, device):
+        bf = lambda t: t.to(device=device, dtype=torch.bfloat16).contiguous()
+        f32 = lambda t: t.to(device=device, dtype=torch.float32).contiguous()
+        self.ln_g = [f32(sd[f'{p}.norm{i}.weight']) for i in range(1, 6)]
+        self.ln_b = [f32(sd[f'{p}.norm{i}.bias']) for i in range(1, 6)]
+        self.ffn = []
+        for name in ('ffn1', 'ffn2'):
+            self.ffn.append(dict(w1=bf(sd[f'{p}.{name}.ln1.weight']), b1=f32(sd[f'{p}.{name}.ln1.bias']),
+                                 w2=bf(sd[f'{p}.{name}.ln2.weight']), b2=f32(sd[f'{p}.{name}.ln2.bias'])))
+        self.w_qkv = bf(torch.cat([sd[f'{p}.att.to_q.weight'], sd[f'{p}.att.to_kv.weight']], dim=0))
+        self.w_out = bf(sd[f'{p}.att.to_out.0.weight'])
+        self.b_out = f32(sd[f'{p}.att.to_out.0.bias'])
+        self.w_pw1 = bf(glu_pack_rows(sd[f'{p}.conv.pointwise_conv1.weight'][:, :, 0]))
+        self.b_pw1 = f32(glu_pack_rows(sd[f'{p}.conv.pointwise_conv1.bias']))
+        scale = sd[f'{p}.conv.norm.weight'].double() / torch.sqrt(sd[f'{p}.conv.norm.running_var'].double() + BN_EPS)
+        dw = sd[f'{p}.conv.depthwise_conv.weight'][:, 0, :].double()            # [C, K]
+        self.w_dw = f32((dw * scale[:, None]).t())                              # [K, C]
+        self.b_dw = f32((sd[f'{p}.conv.depthwise_conv.bias'].double() - sd[f'{p}.conv.norm.running_mean'].double())
+                        * scale + sd[f'{p}.conv.norm.bias'].double())
+        self.w_pw2 = bf(sd[f'{p}.conv.pointwise_conv2.weight'][:, :, 0])
+        self.b_pw2 = f32(sd[f'{p}.conv.pointwise_conv2.bias'])
+
+
+class ModelWeights:
+    """All device tensors of Gmidi_conform (Gconform.py:92-140); index 0 = midi stream (att1), 1 = bound (att2)."""
+
+    def __init__(self, sd, config: dict, device):
+        args = config['midi_extractor_args']
+        self.lay = args['lay']
+        self.outdim = config['midi_num_bins']
+        bf = lambda t: t.to(device=device, dtype=torch.bfloat16).contiguous()
+        f32 = lambda t: t.to(device=device, dtype=torch.float32).contiguous()
+        self.w_in = [bf(sd['model.inln.weight']), bf(sd['model.inln1.weight'])]
+        self.b_in = [f32(sd['model.inln.bias']), f32(sd['model.inln1.bias'])]
+        self.blocks: List[List[BlockWeights]] = []      # [lay + 1][2]
+        self.glu_w, self.glu_b = [], []                 # [lay][2]: index 0 = glu1 (fed by midi), 1 = glu2 (fed by bound)
+        for i in range(self.lay):
+            p = f'model.cf_lay.{i}'
+            self.blocks.append([BlockWeights(sd, p + '.att1', device), BlockWeights(sd, p + '.att2', device)])
+            self.glu_w.append([bf(glu_pack_rows(sd[p + '.glu1.0.weight'])), bf(glu_pack_rows(sd[p + '.glu2.0.weight']))])
+            self.glu_b.append([f32(glu_pack_rows(sd[p + '.glu1.0.bias'])), f32(glu_pack_rows(sd[p + '.glu2.0.bias']))])
+        self.blocks.append([BlockWeights(sd, 'model.att1', device), BlockWeights(sd, 'model.att2', device)])
+        self.w_head = bf(sd['model.outln.weight'])                       # [outdim, 512]
+        self.b_head = f32(_pad32(sd['model.outln.bias']))
+        self.w_cut = f32(sd['model.cutheard.weight'][0])                 # [512]
+        self.b_cut = float(sd['model.cutheard.bias'][0])
+        assert self.w_in[0].shape == (DIM, config['units_dim'])
