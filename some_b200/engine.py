@@ -61,6 +61,43 @@ class Engine:
         self.timestep = config['hop_size'] / config['audio_sample_rate']
         self._ws: Optional[_Workspace] = None
         self.launches = 0
+        # optional per-kernel timing: name -> [(start_event, end_event, work)] where work = FLOPs (GEMM,
+        # attention) or algorithmic bytes (HBM-bound kernels); enabled by bench.py via start_profile()
+        self.prof: Optional[dict] = None
+
+    def start_profile(self):
+        self.prof = {}
+
+    def stop_profile(self) -> Dict[str, dict]:
+        """Returns {kernel: {launches, ms, work}} from the CUDA events recorded since start_profile()."""
+        torch.cuda.synchronize(self.device)
+        out = {}
+        for name, recs in (self.prof or {}).items():
+            out[name] = {'launches': len(recs), 'ms': float(sum(a.elapsed_time(b) for a, b, _ in recs)),
+                         'work': float(sum(w for _, _, w in recs))}
+        self.prof = None
+        return out
+
+    def _mark(self, name: str, work: float):
+        """Context manager: CUDA events on the launching stream around one kernel launch."""
+        eng = self
+
+        class _M:
+            def __enter__(self_m):
+                if eng.prof is not None:
+                    self_m.a = torch.cuda.Event(enable_timing=True)
+                    self_m.b = torch.cuda.Event(enable_timing=True)
+                    self_m.a.record(torch.cuda.current_stream(eng.device))
+                return self_m
+
+            def __exit__(self_m, *exc):
+                if eng.prof is not None:
+                    self_m.b.record(torch.cuda.current_stream(eng.device))
+                    eng.prof.setdefault(name, []).append((self_m.a, self_m.b, work))
+                eng.launches += 1
+                return False
+
+        return _M()
 
     # ------------------------------------------------------------------ helpers
     @property
@@ -78,8 +115,8 @@ class Engine:
         g.A, g.W = _lib.pair(a0, a1), _lib.pair(w0, w1)
         g.bias, g.out, g.resid = _lib.pair(b0, b1), _lib.pair(out0, out1), _lib.pair(r0, r1)
         g.groups, g.M, g.N, g.K, g.lda, g.ld_out, g.epilogue, g.alpha = groups, m, n, k, lda, ld_out, epi, alpha
-        _lib.check(self.lib.some_gemm(C.byref(g), self._stream), 'some_gemm')
-        self.launches += 1
+        with self._mark('some_gemm', 2.0 * m * n * k * groups):
+            _lib.check(self.lib.some_gemm(C.byref(g), self._stream), 'some_gemm')
 
     def _ln(self, x, gamma, beta, out_bf16, out_f32, m):
         a = _lib.LnArgs()
@@ -88,20 +125,22 @@ class Engine:
         a.out_bf16 = _lib.pair(out_bf16[0], out_bf16[1]) if out_bf16 is not None else (C.c_void_p * 2)()
         a.out_f32 = _lib.pair(out_f32[0], out_f32[1]) if out_f32 is not None else (C.c_void_p * 2)()
         a.groups, a.M = 2, m
-        _lib.check(self.lib.some_layernorm(C.byref(a), self._stream), 'some_layernorm')
-        self.launches += 1
+        nout = (2 if out_bf16 is not None else 0) + (4 if out_f32 is not None else 0)
+        with self._mark('some_layernorm', 2.0 * m * DIM * (4 + nout)):
+            _lib.check(self.lib.some_layernorm(C.byref(a), self._stream), 'some_layernorm')
 
     # ------------------------------------------------------------------ stages
     def run_mel(self, wave: torch.Tensor, clip_start: torch.Tensor, clip_len: torch.Tensor, cu_frames: torch.Tensor,
                 b: int, max_frames: int, out_f32: Optional[torch.Tensor], out_bf16: Optional[torch.Tensor]):
         """K-mel (spec.py:38-72).  wave f32; clip i = wave[start_i : start_i + len_i]; outputs [M, 80]."""
         t = self.mel
-        _lib.check(self.lib.some_mel_logmel(
-            wave.data_ptr(), clip_start.data_ptr(), clip_len.data_ptr(), cu_frames.data_ptr(), b, max_frames,
-            t['mel_start'].data_ptr(), t['mel_count'].data_ptr(), t['mel_weights'].data_ptr(),
-            t['twiddle'].data_ptr(), t['window'].data_ptr(), _lib.ptr(out_f32), _lib.ptr(out_bf16),
-            1e-5, self._stream), 'some_mel_logmel')
-        self.launches += 1
+        m = (out_f32 if out_f32 is not None else out_bf16).shape[0]
+        with self._mark('some_mel_logmel', m * (512 * 4 + 80 * 4.0)):        # 2368 B / frame (SURVEY.md §8d)
+            _lib.check(self.lib.some_mel_logmel(
+                wave.data_ptr(), clip_start.data_ptr(), clip_len.data_ptr(), cu_frames.data_ptr(), b, max_frames,
+                t['mel_start'].data_ptr(), t['mel_count'].data_ptr(), t['mel_weights'].data_ptr(),
+                t['twiddle'].data_ptr(), t['window'].data_ptr(), _lib.ptr(out_f32), _lib.ptr(out_bf16),
+                1e-5, self._stream), 'some_mel_logmel')
 
     def _block(self, ws: _Workspace, blk, m: int, b: int, cu_frames, max_frames: int, last: bool):
         x, a, h, qkv, g = ws.x, ws.a, ws.h, ws.qkv, ws.g
@@ -126,8 +165,8 @@ class Engine:
         at = _lib.AttnArgs()
         at.qkv, at.out = _lib.pair(qkv[0], qkv[1]), _lib.pair(a[0], a[1])
         at.groups, at.B, at.cu_frames, at.max_frames = 2, b, cu_frames.data_ptr(), max_frames
-        _lib.check(lib.some_attention_varlen(C.byref(at), st), 'some_attention_varlen')
-        self.launches += 1
+        with self._mark('some_attention_varlen', 2.0 * self._att_flops):
+            _lib.check(lib.some_attention_varlen(C.byref(at), st), 'some_attention_varlen')
         self._gemm(a[0], a[1], w0.w_out, w1.w_out, w0.b_out, w1.b_out, x[0], x[1], x[0], x[1],
                    m, DIM, DIM, DIM, DIM, _lib.EPI_RESID_F32)                   # :60
         ln(2)
@@ -137,8 +176,8 @@ class Engine:
         dw.x, dw.w, dw.b = _lib.pair(g[0], g[1]), _lib.pair(w0.w_dw, w1.w_dw), _lib.pair(w0.b_dw, w1.b_dw)
         dw.out = _lib.pair(a[0], a[1])
         dw.groups, dw.B, dw.cu_frames, dw.max_frames = 2, b, cu_frames.data_ptr(), max_frames
-        _lib.check(lib.some_dwconv_bn_silu(C.byref(dw), st), 'some_dwconv_bn_silu')   # base_conv.py:66-68
-        self.launches += 1
+        with self._mark('some_dwconv_bn_silu', 2.0 * m * DIM * 4):               # bf16 in + bf16 out
+            _lib.check(lib.some_dwconv_bn_silu(C.byref(dw), st), 'some_dwconv_bn_silu')   # base_conv.py:66-68
         self._gemm(a[0], a[1], w0.w_pw2, w1.w_pw2, w0.b_pw2, w1.b_pw2, x[0], x[1], x[0], x[1],
                    m, DIM, DIM, DIM, DIM, _lib.EPI_RESID_F32)                   # base_conv.py:69 + Gconform.py:61
         ln(3)
@@ -151,11 +190,12 @@ class Engine:
             al.x, al.gamma, al.beta = _lib.pair(x[0]), _lib.pair(w0.ln_g[4]), _lib.pair(w0.ln_b[4])
             al.out_bf16, al.out_f32 = _lib.pair(a[0]), (C.c_void_p * 2)()
             al.groups, al.M = 1, m
-            _lib.check(lib.some_layernorm(C.byref(al), st), 'some_layernorm')
-            _lib.check(lib.some_bound_head(x[1].data_ptr(), w1.ln_g[4].data_ptr(), w1.ln_b[4].data_ptr(),
-                                           self.w.w_cut.data_ptr(), self.w.b_cut, m, ws.bounds.data_ptr(), st),
-                       'some_bound_head')
-            self.launches += 2
+            with self._mark('some_layernorm', m * DIM * 6.0):
+                _lib.check(lib.some_layernorm(C.byref(al), st), 'some_layernorm')
+            with self._mark('some_bound_head', m * DIM * 4.0):
+                _lib.check(lib.some_bound_head(x[1].data_ptr(), w1.ln_g[4].data_ptr(), w1.ln_b[4].data_ptr(),
+                                               self.w.w_cut.data_ptr(), self.w.b_cut, m, ws.bounds.data_ptr(), st),
+                           'some_bound_head')
 
     def run_trunk(self, ws: _Workspace, m: int, b: int, cu_frames: torch.Tensor, max_frames: int,
                   head: str = 'sigmoid', taps: Optional[dict] = None):
@@ -163,6 +203,11 @@ class Engine:
         (Gmidi_conform.py:30-40).  Reads ws.units; writes ws.probs [m, outdim] and ws.bounds [m].
         head: 'sigmoid' | 'softmax' | 'logits'."""
         w, x, a = self.w, ws.x, ws.a
+        if self.prof is not None:   # QK^T + PV MACs of one attention launch (both streams): 2 * 8 * 64 * sum T^2
+            t = torch.diff(cu_frames).double()
+            self._att_flops = float(2 * 2 * 512 * (t * t).sum().item())
+        else:
+            self._att_flops = 0.0
         self._gemm(ws.units, ws.units, w.w_in[0], w.w_in[1], w.b_in[0], w.b_in[1], x[0], x[1], None, None,
                    m, DIM, 80, 80, DIM, _lib.EPI_BIAS_F32)                       # inln / inln1
         for i in range(w.lay):
@@ -197,8 +242,8 @@ class Engine:
             dbg['rest'] = torch.zeros(m, dtype=torch.uint8, device=self.device)
             d.dbg_frame2item, d.dbg_values, d.dbg_rest = (dbg[k].data_ptr() for k in ('frame2item', 'values', 'rest'))
         d.scratch = ws.scratch.data_ptr()
-        _lib.check(self.lib.some_decode_notes(C.byref(d), self._stream), 'some_decode_notes')
-        self.launches += 1
+        with self._mark('some_decode_notes', m * (self.outdim * 4.0 + 4.0)):
+            _lib.check(self.lib.some_decode_notes(C.byref(d), self._stream), 'some_decode_notes')
 
     # ------------------------------------------------------------------ public batched entry point
     def pack(self, waveforms: Sequence[np.ndarray]):

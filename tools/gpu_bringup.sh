@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 for t in "$@"; do
   name=$(echo "$t" | tr '/:[] ' '_____')
   echo "=== $t" | tee -a gpurun_out/bringup.log
-  timeout 300 python -m pytest "$t" -x -q -m gpu -s --no-header -p no:cacheprovider > gpurun_out/bringup_$name.log 2>&1
+  timeout 300 python -m pytest $t -x -q -m gpu -s --no-header -p no:cacheprovider > gpurun_out/bringup_$name.log 2>&1
   echo "exit=$?" | tee -a gpurun_out/bringup.log
   tail -n 25 gpurun_out/bringup_$name.log | tee -a gpurun_out/bringup.log
 done
