@@ -224,7 +224,7 @@ class Engine:
                    m, self.outdim, DIM, DIM, self.outdim, epi, groups=1)          # outln (+ sigmoid / softmax)
 
     def run_decode(self, ws: _Workspace, m: int, b: int, cu_frames: torch.Tensor, note_count: torch.Tensor,
-                   quantized: bool, dbg: Optional[dict] = None, probs=None, bounds=None):
+                   quantized: bool, dbg: Optional[dict] = None, probs=None, bounds=None, out=None):
         cfg = self.config
         d = _lib.DecodeArgs()
         d.probs = (probs if probs is not None else ws.probs).data_ptr()
@@ -234,7 +234,8 @@ class Engine:
         d.vmin, d.vmax = float(cfg['midi_min']), float(cfg['midi_max'])
         d.deviation = float(cfg.get('midi_prob_deviation', 1.0))
         d.threshold = float(cfg.get('rest_threshold', 0.1))
-        d.note_midi, d.note_dur, d.note_rest = ws.note_midi.data_ptr(), ws.note_dur.data_ptr(), ws.note_rest.data_ptr()
+        nm_t, nd_t, nr_t = out if out is not None else (ws.note_midi, ws.note_dur, ws.note_rest)
+        d.note_midi, d.note_dur, d.note_rest = nm_t.data_ptr(), nd_t.data_ptr(), nr_t.data_ptr()
         d.note_count = note_count.data_ptr()
         if dbg is not None:
             dbg['frame2item'] = torch.zeros(m, dtype=torch.int32, device=self.device)
@@ -246,54 +247,97 @@ class Engine:
             _lib.check(self.lib.some_decode_notes(C.byref(d), self._stream), 'some_decode_notes')
 
     # ------------------------------------------------------------------ public batched entry point
-    def pack(self, waveforms: Sequence[np.ndarray]):
-        """Concatenates clips into one pinned host buffer (each clip start 16-byte aligned) and builds the
-        var-len tables [starts | lens] (int64) and cu_frames (int32).  Host only."""
-        b = len(waveforms)
-        lens = np.array([int(w.shape[0]) for w in waveforms], dtype=np.int64)
+    def tables(self, lens: np.ndarray):
+        """Var-len tables for clips of ``lens`` samples: 16-byte aligned starts, cu_frames (T = 1 + L // hop,
+        spec.py:48-60).  Host only."""
+        lens = np.asarray(lens, dtype=np.int64)
         padded = (lens + 3) & ~3
-        starts = np.zeros(b, dtype=np.int64)
+        starts = np.zeros(len(lens), dtype=np.int64)
         np.cumsum(padded[:-1], out=starts[1:])
-        total = int(padded.sum())
+        cu = np.zeros(len(lens) + 1, dtype=np.int32)
+        np.cumsum(1 + lens // HOP, out=cu[1:])
+        return starts, lens, cu, int(padded.sum())
+
+    def pack(self, waveforms: Sequence[np.ndarray]):
+        """Concatenates clips into one pinned host buffer (test / bench helper).  Returns
+        (pinned wave f32, pinned [starts | lens] int64, cu_frames int32 numpy)."""
+        starts, lens, cu, total = self.tables([int(w.shape[0]) for w in waveforms])
         host = torch.empty(max(total, 4), dtype=torch.float32).pin_memory()
-        hv = host.numpy()
-        for s, w, n, pn in zip(starts, waveforms, lens, padded):
-            hv[s:s + n] = w
-            hv[s + n:s + pn] = 0.0
-        cu = np.zeros(b + 1, dtype=np.int32)
-        np.cumsum(1 + lens // HOP, out=cu[1:])                  # T = 1 + L // hop (spec.py:48-60)
+        for s, w, n in zip(starts, waveforms, lens):
+            host[s:s + n].copy_(torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32)))
         tables = torch.from_numpy(np.concatenate([starts, lens])).pin_memory()
         return host, tables, cu
+
+    def _staging(self, total: int, b: int, m: int):
+        """Grow-only pinned staging + device input buffers (cudaHostAlloc per call would dominate the step)."""
+        st = getattr(self, '_stage', None)
+        if st is None or st['wave_h'].numel() < total or st['tab_h'].numel() < 3 * b + 1 or st['out_h'].numel() < 9 * m + 4 * b:
+            cap_w = max(total, 4, int(1.25 * st['wave_h'].numel()) if st else 0)
+            cap_b = max(3 * b + 1, st['tab_h'].numel() if st else 0)
+            cap_o = max(9 * m + 4 * b, int(1.25 * st['out_h'].numel()) if st else 0)
+            st = {
+                'wave_h': torch.empty(cap_w, dtype=torch.float32).pin_memory(),
+                'wave_d': torch.empty(cap_w, dtype=torch.float32, device=self.device),
+                'tab_h': torch.empty(cap_b, dtype=torch.int64).pin_memory(),
+                'tab_d': torch.empty(cap_b, dtype=torch.int64, device=self.device),
+                'out_h': torch.empty(cap_o, dtype=torch.uint8).pin_memory(),
+                'out_d': torch.empty(cap_o, dtype=torch.uint8, device=self.device),
+            }
+            self._stage = st
+        return st
 
     def infer(self, waveforms: Sequence[np.ndarray], quantized: bool = False,
               return_intermediates: bool = False) -> List[Dict[str, np.ndarray]]:
         """waveform-in -> notes-out for a list of clips: the batched equivalent of BaseInference.infer
-        (base_infer.py:46-53).  One H2D copy of the audio, one packed D2H of the notes."""
+        (base_infer.py:46-53).  Host buffers in, host buffers out: every clip is staged through pinned memory
+        and copied H2D asynchronously while the next one is being staged; the notes of the whole batch come
+        back in ONE packed D2H copy [counts | dur | midi | rest]."""
         b = len(waveforms)
         if b == 0:
             return []
-        host, tables, cu = self.pack(waveforms)
+        starts, lens, cu, total = self.tables([int(w.shape[0]) for w in waveforms])
         m, max_frames = int(cu[-1]), int(np.diff(cu).max())
         dev = self.device
         with torch.cuda.device(dev):
-            wave = host.to(dev, non_blocking=True)
-            tables_d = tables.to(dev, non_blocking=True)
-            cu_d = torch.from_numpy(cu).pin_memory().to(dev, non_blocking=True)
+            st = self._staging(total, b, m)
+            stream = torch.cuda.current_stream(dev)
+            wave_h, wave_d = st['wave_h'], st['wave_d']
+            for s, w, n in zip(starts, waveforms, lens):
+                if n == 0:
+                    continue
+                src = torch.from_numpy(w if (w.dtype == np.float32 and w.flags.c_contiguous)
+                                       else np.ascontiguousarray(w, dtype=np.float32))
+                wave_h[s:s + n].copy_(src)                                      # multi-threaded host memcpy
+                wave_d[s:s + n].copy_(wave_h[s:s + n], non_blocking=True)       # async DMA overlaps the next memcpy
+            tab_h = st['tab_h']
+            tab_h[:b] = torch.from_numpy(starts)
+            tab_h[b:2 * b] = torch.from_numpy(lens)
+            tab_h[2 * b:3 * b + 1] = torch.from_numpy(cu.astype(np.int64))
+            st['tab_d'][:3 * b + 1].copy_(tab_h[:3 * b + 1], non_blocking=True)
+            cu_d = st['tab_d'][2 * b:3 * b + 1].to(torch.int32)
             ws = self.workspace(m)
-            note_count = torch.empty(b, dtype=torch.int32, device=dev)
+            # decode writes straight into the packed D2H slab: [counts i32 [b] | dur i32 [m] | midi f32 [m] | rest u8 [m]]
+            out_d = st['out_d']
+            note_count = out_d[:4 * b].view(torch.int32)
+            note_dur = out_d[4 * b:4 * b + 4 * m].view(torch.int32)
+            note_midi = out_d[4 * b + 4 * m:4 * b + 8 * m].view(torch.float32)
+            note_rest = out_d[4 * b + 8 * m:4 * b + 9 * m]
             mel_f32 = torch.empty((m, 80), dtype=torch.float32, device=dev) if return_intermediates else None
-            self.run_mel(wave, tables_d[:b], tables_d[b:], cu_d, b, max_frames, mel_f32, ws.units)
+            self.run_mel(wave_d, st['tab_d'][:b], st['tab_d'][b:2 * b], cu_d, b, max_frames, mel_f32, ws.units)
             self.run_trunk(ws, m, b, cu_d, max_frames, 'softmax' if quantized else 'sigmoid')
-            self.run_decode(ws, m, b, cu_d, note_count, quantized)
-            nm = ws.note_midi[:m].to('cpu', non_blocking=True)
-            nd = ws.note_dur[:m].to('cpu', non_blocking=True)
-            nr = ws.note_rest[:m].to('cpu', non_blocking=True)
-            nc = note_count.to('cpu', non_blocking=True)
+            self.run_decode(ws, m, b, cu_d, note_count, quantized, out=(note_midi, note_dur, note_rest))
+            nbytes = 4 * b + 9 * m
+            st['out_h'][:nbytes].copy_(out_d[:nbytes], non_blocking=True)
             extra = None
             if return_intermediates:
                 extra = (mel_f32.cpu(), ws.probs[:m].cpu(), ws.bounds[:m].cpu())
-            torch.cuda.current_stream(dev).synchronize()
-        return self.unpack(cu, nc.numpy(), nm.numpy(), nd.numpy(), nr.numpy(), extra)
+            stream.synchronize()
+            host = st['out_h'][:nbytes].numpy()
+            nc = host[:4 * b].view(np.int32)
+            nd = host[4 * b:4 * b + 4 * m].view(np.int32)
+            nm = host[4 * b + 4 * m:4 * b + 8 * m].view(np.float32)
+            nr = host[4 * b + 8 * m:4 * b + 9 * m]
+            return self.unpack(cu, nc, nm, nd, nr, extra)
 
     def unpack(self, cu, nc, nm, nd, nr, extra=None) -> List[Dict[str, np.ndarray]]:
         out = []

@@ -1,0 +1,228 @@
+"""CPU-only tests of the host logic: the C-ABI library loads and exports every symbol the header declares,
+config flattening / strict checkpoint schema, weight packing (GLU interleave, BN folding, mel tables),
+clip sharding + the gloo all-gather of note records (world_size 2), and the drop-in package alias."""
+import os
+import pathlib
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+from some_b200 import config as sconfig
+from some_b200 import dist as sdist
+from some_b200 import synth, weights
+
+REPO = pathlib.Path(__file__).resolve().parent.parent
+
+
+# --------------------------------------------------------------------------- C ABI
+def test_library_exports_every_declared_symbol():
+    from some_b200 import _lib
+    lib = _lib.load()                        # raises if libsome_b200.so has not been built
+    header = (REPO / 'include' / 'some_b200.h').read_text()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    declared = set(re.findall(r'\b(some_[a-z0-9_]+)\s*\(', header))
+    assert declared == set(_lib.EXPORTS), (declared ^ set(_lib.EXPORTS))
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/some_b200.h but not exported'
+    assert lib.some_version() == 100
+    assert lib.some_last_error() is not None
+
+
+def test_abi_struct_sizes_match_header_layout():
+    """ctypes mirrors of the header structs: pointer arrays first, then ints (catches field drift)."""
+    from some_b200 import _lib
+    import ctypes as C
+    assert C.sizeof(_lib.GemmArgs) == 10 * 8 + 7 * 4 + 4
+    assert C.sizeof(_lib.LnArgs) == 10 * 8 + 2 * 4
+    assert C.sizeof(_lib.AttnArgs) == 4 * 8 + 2 * 4 + 8 + 4 + 4     # + tail padding
+    assert C.sizeof(_lib.DwconvArgs) == 8 * 8 + 2 * 4 + 8 + 4 + 4
+    assert C.sizeof(_lib.DecodeArgs) == 3 * 8 + 4 * 4 + 4 * 4 + 8 * 8
+
+
+def test_engine_refuses_cpu():
+    from some_b200 import _lib, plugin
+    cfg = synth.named_config('two_head')
+    with pytest.raises(_lib.SomeB200Error):
+        plugin.MIDIExtractionInference(config=cfg, model_path=pathlib.Path('/nonexistent.ckpt'), device='cpu')
+
+
+# --------------------------------------------------------------------------- config / checkpoint schema
+def test_flatten_config_chain(tmp_path):
+    (tmp_path / 'configs').mkdir()
+    (tmp_path / 'configs' / 'base.yaml').write_text(yaml.safe_dump({'a': 1, 'd': {'x': 1, 'y': 2}, 'keep': 7}))
+    (tmp_path / 'configs' / 'mid.yaml').write_text(yaml.safe_dump({'base_config': 'configs/base.yaml', 'a': 2, 'd': {'y': 3}}))
+    (tmp_path / 'configs' / 'top.yaml').write_text(yaml.safe_dump({'base_config': ['configs/mid.yaml'], 'd': {'z': 4}}))
+    flat = sconfig.flatten_config(tmp_path / 'configs' / 'top.yaml', root=tmp_path)
+    assert flat == {'a': 2, 'd': {'x': 1, 'y': 3, 'z': 4}, 'keep': 7}
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize('name,key', [('two_head_model', 'two_head'), ('midi_conformer', 'midi_conformer'),
+                                      ('quant_two_head_model', 'quant_two_head')])
+def test_named_configs_match_reference_yaml(name, key):
+    flat = sconfig.flatten_config(f'/root/reference/configs/{name}.yaml', root='/root/reference')
+    mine = synth.named_config(key)
+    for k, v in mine.items():
+        if k in ('midi_prob_deviation', 'rest_threshold') and key == 'quant_two_head':
+            assert k not in flat          # the stock chain lacks them (SURVEY.md discrepancy 6); injected by the harness
+            continue
+        assert flat[k] == v, (k, flat[k], v)
+
+
+def test_state_dict_schema_and_strict_loading(tmp_path):
+    cfg = synth.named_config('two_head', lay=1)
+    ckpt = synth.write_checkpoint(tmp_path, cfg, seed=3)
+    sd = sconfig.load_state_dict_strict(ckpt, cfg)
+    assert list(sd) == list(sconfig.model_param_shapes(cfg))
+    n_params = sum(int(np.prod(v.shape)) for k, v in sd.items() if 'num_batches' not in k and 'running' not in k)
+    assert n_params == 4 * 6059008 + 2 * (1024 * 512 + 1024) + 2 * (512 * 80 + 512) + 128 * 512 + 128 + 512 + 1
+    raw = torch.load(ckpt, weights_only=False)
+    raw['state_dict'].pop('model.model.inln.bias')
+    raw['state_dict']['model.model.bogus'] = torch.zeros(1)
+    torch.save(raw, tmp_path / 'bad.ckpt')
+    with pytest.raises(RuntimeError, match='Missing key.*inln.bias'):
+        sconfig.load_state_dict_strict(tmp_path / 'bad.ckpt', cfg)
+    with pytest.raises(NotImplementedError):
+        sconfig.check_supported(dict(cfg, units_dim=768))
+
+
+@pytest.mark.reference
+def test_schema_matches_reference_module():
+    sys.path.insert(0, '/root/reference')
+    try:
+        from modules.model.Gmidi_conform import midi_conforms
+    finally:
+        sys.path.remove('/root/reference')
+    cfg = synth.named_config('two_head')
+    ref = midi_conforms({'midi_extractor_args': dict(cfg['midi_extractor_args']), 'units_dim': 80,
+                         'midi_num_bins': 128}).state_dict()
+    mine = sconfig.model_param_shapes(cfg)
+    assert set(ref) == set(mine)
+    for k, v in ref.items():
+        assert tuple(v.shape) == tuple(mine[k]), k
+    ref.update(synth.fabricate_state_dict(cfg))      # and the fabricated weights load strictly
+
+
+# --------------------------------------------------------------------------- weight packing
+def test_glu_pack_rows_roundtrip():
+    w = torch.arange(1024 * 3, dtype=torch.float32).reshape(1024, 3)
+    p = weights.glu_pack_rows(w)
+    for j in (0, 5, 31):
+        assert torch.equal(p[32 * j:32 * j + 16], w[16 * j:16 * j + 16])
+        assert torch.equal(p[32 * j + 16:32 * j + 32], w[512 + 16 * j:512 + 16 * j + 16])
+
+
+def test_bn_folding_and_packing_match_torch():
+    cfg = synth.named_config('two_head', lay=1)
+    sd = synth.fabricate_state_dict(cfg, seed=11)
+    p = 'model.att1'
+    bw = weights.BlockWeights(sd, p, 'cpu')
+    x = torch.randn(1, 512, 50)
+    ref = torch.nn.functional.batch_norm(
+        torch.nn.functional.conv1d(x, sd[p + '.conv.depthwise_conv.weight'], sd[p + '.conv.depthwise_conv.bias'],
+                                   padding=15, groups=512),
+        sd[p + '.conv.norm.running_mean'], sd[p + '.conv.norm.running_var'], sd[p + '.conv.norm.weight'],
+        sd[p + '.conv.norm.bias'], False, 0.1, 1e-5)
+    got = torch.nn.functional.conv1d(x, bw.w_dw.t().unsqueeze(1), bw.b_dw, padding=15, groups=512)
+    torch.testing.assert_close(got, ref, atol=1e-5, rtol=1e-5)
+    assert bw.w_qkv.shape == (1536, 512) and bw.w_qkv.dtype == torch.bfloat16
+    assert torch.equal(bw.w_qkv[:512].float(), sd[p + '.att.to_q.weight'].bfloat16().float())
+    assert torch.equal(bw.w_qkv[512:].float(), sd[p + '.att.to_kv.weight'].bfloat16().float())
+
+
+def test_mel_tables_match_golden_basis(golden_dir):
+    cfg = synth.named_config('two_head')
+    t = weights.mel_tables(cfg, 'cpu')
+    ref = np.load(golden_dir / 'mel.npz')['mel_basis']          # buffer of the reference's MelSpectrogram
+    assert np.array_equal(t['bank'], ref)
+    dense = np.zeros_like(ref)
+    for m in range(80):
+        s, c = int(t['mel_start'][m]), int(t['mel_count'][m])
+        dense[m, s:s + c] = t['mel_weights'][m, :c].numpy()
+    assert np.array_equal(dense, ref)
+    assert torch.equal(t['window'], torch.hann_window(2048))
+    tw = t['twiddle'].double()
+    assert abs(float(tw[512, 0])) < 1e-7 and abs(float(tw[512, 1]) + 1.0) < 1e-7    # W^(N/4) = -i
+
+
+# --------------------------------------------------------------------------- sharding + gather
+def test_shard_clips_balanced_and_complete():
+    rng = np.random.default_rng(0)
+    lengths = [int(x) for x in rng.integers(44100 * 5, 44100 * 15, size=37)] + [44100 * 300]
+    for world in (1, 2, 4, 8):
+        shards = sdist.shard_clips(lengths, world)
+        assert sorted(i for s in shards for i in s) == list(range(len(lengths)))
+        loads = [sum(sdist.clip_cost(lengths[i]) for i in s) for s in shards]
+        biggest = max(sdist.clip_cost(n) for n in lengths)
+        assert max(loads) - min(loads) <= biggest + 1e-6        # LPT bound
+
+
+def _fake_notes(n_samples):
+    t = 1 + n_samples // 512
+    rng = np.random.default_rng(n_samples)
+    n = int(rng.integers(1, t + 1))
+    dur = rng.multinomial(t, np.ones(n) / n).astype(np.int64)
+    return {'note_midi': rng.uniform(30, 90, n).astype(np.float32), 'note_dur': dur * (512 / 44100),
+            'note_rest': rng.random(n) < 0.2}
+
+
+def test_pack_unpack_roundtrip():
+    lengths = [5000, 300, 44100, 0]
+    res = [_fake_notes(n) for n in lengths]
+    frames = [1 + n // 512 for n in lengths]
+    slab = sdist.pack_results(res, frames, sdist.slab_bytes(lengths, [list(range(4))]), 512 / 44100)
+    back = sdist.unpack_results(slab, frames, 512 / 44100)
+    for a, b in zip(res, back):
+        for k in a:
+            np.testing.assert_array_equal(a[k], b[k])
+
+
+def _gloo_worker(rank, world, port, lengths, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+
+    class FakePlugin:
+        timestep = 512 / 44100
+
+        def infer(self, waves):
+            return [_fake_notes(len(w)) for w in waves]
+
+    waves = [np.zeros(n, dtype=np.float32) for n in lengths]
+    merged = sdist.infer_sharded(FakePlugin(), waves)
+    ok = all(np.array_equal(m[k], _fake_notes(n)[k]) for m, n in zip(merged, lengths) for k in m)
+    q.put((rank, ok, len(merged)))
+    dist.destroy_process_group()
+
+
+def test_infer_sharded_gloo_world2():
+    import torch.multiprocessing as mp
+    lengths = [44100, 512 * 7 + 3, 90000, 1000, 250000, 0, 333]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, lengths, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r[0] for r in results) == [0, 1]
+    assert all(ok and n == len(lengths) for _, ok, n in results)
+
+
+# --------------------------------------------------------------------------- drop-in alias
+def test_inference_package_is_the_drop_in():
+    code = ("import inference, some_b200.plugin as p; "
+            "assert inference.MIDIExtractionInference is p.MIDIExtractionInference; "
+            "assert issubclass(inference.QuantizedMIDIExtractionInference, inference.BaseInference); "
+            "assert inference.task_inference_mapping['training.MIDIExtractionTask'] == 'inference.MIDIExtractionInference'; "
+            "print('ok')")
+    env = dict(os.environ, PYTHONPATH=f'{REPO}:/root/reference')
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, cwd='/tmp')
+    assert out.returncode == 0 and 'ok' in out.stdout, out.stderr
