@@ -9,7 +9,8 @@
 // keys double-buffered in shared memory with cp.async (zero-fill beyond the clip), XOR-swizzled 128-B rows
 // for conflict-free ldmatrix; S and O accumulate in fp32 registers, online softmax in base 2.
 // Tensor path: mma.sync.m16n8k16 bf16 (legacy HMMA path).
-// TODO(round 2): move QK^T / PV to tcgen05 with S/O in TMEM (sm100_ptx.cuh has the MN-major descriptor for V).
+// Superseded on the product path by attention_tc.cu (tcgen05); exported as some_attention_varlen_mma and used by the
+// tests as an independent cross-check of the tensor-core kernel.
 #include "host_common.h"
 #include "sm100_ptx.cuh"
 
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
 
 using namespace some;
 
-extern "C" int some_attention_varlen(const some_attn_args* a, cudaStream_t stream) {
+extern "C" int some_attention_varlen_mma(const some_attn_args* a, cudaStream_t stream) {
   SOME_REQUIRE(a != nullptr && (a->groups == 1 || a->groups == 2), "some_attention_varlen: bad args");
   if (a->B <= 0 || a->max_frames <= 0) return 0;
   SOME_REQUIRE(a->cu_frames != nullptr, "some_attention_varlen: null cu_frames");

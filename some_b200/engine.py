@@ -164,7 +164,7 @@ class Engine:
                    m, 3 * DIM, DIM, DIM, 3 * DIM, _lib.EPI_STORE_BF16)
         at = _lib.AttnArgs()
         at.qkv, at.out = _lib.pair(qkv[0], qkv[1]), _lib.pair(a[0], a[1])
-        at.groups, at.B, at.cu_frames, at.max_frames = 2, b, cu_frames.data_ptr(), max_frames
+        at.groups, at.B, at.M, at.cu_frames, at.max_frames = 2, b, m, cu_frames.data_ptr(), max_frames
         with self._mark('some_attention_varlen', 2.0 * self._att_flops):
             _lib.check(lib.some_attention_varlen(C.byref(at), st), 'some_attention_varlen')
         self._gemm(a[0], a[1], w0.w_out, w1.w_out, w0.b_out, w1.b_out, x[0], x[1], x[0], x[1],

@@ -185,8 +185,9 @@ def test_dwconv_bn_silu(lib):
             r0 += t
 
 
-@pytest.mark.parametrize('frames', [[1], [64, 65, 127, 128, 129], [700, 3, 259]])
-def test_attention_varlen(lib, frames):
+@pytest.mark.parametrize('impl', ['some_attention_varlen', 'some_attention_varlen_mma'])
+@pytest.mark.parametrize('frames', [[1], [64, 65, 127, 128, 129], [700, 3, 259], [2584]])
+def test_attention_varlen(lib, frames, impl):
     torch.manual_seed(7)
     cu = _cu(frames)
     m = int(cu[-1])
@@ -194,8 +195,8 @@ def test_attention_varlen(lib, frames):
     out = [torch.full((m, 512), float('nan'), device=DEV, dtype=torch.bfloat16) for _ in range(2)]
     a = _lib.AttnArgs()
     a.qkv, a.out = _lib.pair(*qkv), _lib.pair(*out)
-    a.groups, a.B, a.cu_frames, a.max_frames = 2, len(frames), cu.data_ptr(), max(frames)
-    _lib.check(lib.some_attention_varlen(C.byref(a), stream()))
+    a.groups, a.B, a.M, a.cu_frames, a.max_frames = 2, len(frames), m, cu.data_ptr(), max(frames)
+    _lib.check(getattr(lib, impl)(C.byref(a), stream()), impl)
     torch.cuda.synchronize()
     for i in range(2):
         r0 = 0
@@ -217,7 +218,7 @@ def test_mel_matches_torch_stft(lib):
     tabs = mel_tables(cfg, DEV)
     clips = list(synth.edge_case_waveforms().values()) + [synth.synth_waveform(5, seconds=2.0)]
     eng = Engine.__new__(Engine)
-    eng.lib, eng.device, eng.mel, eng.launches = lib, torch.device(DEV), tabs, 0
+    eng.lib, eng.device, eng.mel, eng.launches, eng.prof = lib, torch.device(DEV), tabs, 0, None
     host, tables, cu = Engine.pack(eng, clips)
     b, m = len(clips), int(cu[-1])
     out = torch.full((m, 80), float('nan'), device=DEV)
@@ -258,7 +259,7 @@ def test_decode_matches_oracle(lib, golden_dir):
     m = int(cu[-1])
     cfg = synth.named_config('two_head')
     eng = Engine.__new__(Engine)
-    eng.lib, eng.device, eng.config, eng.outdim, eng.launches = lib, torch.device(DEV), cfg, 128, 0
+    eng.lib, eng.device, eng.config, eng.outdim, eng.launches, eng.prof = lib, torch.device(DEV), cfg, 128, 0, None
     eng.timestep = 512 / 44100
     from some_b200.engine import _Workspace
     ws = _Workspace(m, 128, DEV)

@@ -39,7 +39,7 @@ def test_abi_struct_sizes_match_header_layout():
     import ctypes as C
     assert C.sizeof(_lib.GemmArgs) == 10 * 8 + 7 * 4 + 4
     assert C.sizeof(_lib.LnArgs) == 10 * 8 + 2 * 4
-    assert C.sizeof(_lib.AttnArgs) == 4 * 8 + 2 * 4 + 8 + 4 + 4     # + tail padding
+    assert C.sizeof(_lib.AttnArgs) == 4 * 8 + 3 * 4 + 4 + 8 + 4 + 4  # incl. alignment / tail padding
     assert C.sizeof(_lib.DwconvArgs) == 8 * 8 + 2 * 4 + 8 + 4 + 4
     assert C.sizeof(_lib.DecodeArgs) == 3 * 8 + 4 * 4 + 4 * 4 + 8 * 8
 
