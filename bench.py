@@ -161,7 +161,8 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
     config = synth.named_config(CONFIG_NAME)
-    with tempfile.TemporaryDirectory() as d:
+    import contextlib
+    with tempfile.TemporaryDirectory() as d, contextlib.redirect_stdout(sys.stderr):   # stdout = the ONE JSON line
         ckpt = synth.write_checkpoint(d, config, seed=1234)
         ins = plugin.MIDIExtractionInference(config=config, model_path=ckpt, device=f'cuda:{local_rank}')
     eng = ins.model

@@ -271,10 +271,10 @@ class Engine:
     def _staging(self, total: int, b: int, m: int):
         """Grow-only pinned staging + device input buffers (cudaHostAlloc per call would dominate the step)."""
         st = getattr(self, '_stage', None)
-        if st is None or st['wave_h'].numel() < total or st['tab_h'].numel() < 3 * b + 1 or st['out_h'].numel() < 9 * m + 4 * b:
+        if st is None or st['wave_h'].numel() < total or st['tab_h'].numel() < 4 * b + 8 or st['out_h'].numel() < 9 * m + 4 * b + 64:
             cap_w = max(total, 4, int(1.25 * st['wave_h'].numel()) if st else 0)
-            cap_b = max(3 * b + 1, st['tab_h'].numel() if st else 0)
-            cap_o = max(9 * m + 4 * b, int(1.25 * st['out_h'].numel()) if st else 0)
+            cap_b = max(4 * b + 8, st['tab_h'].numel() if st else 0)
+            cap_o = max(9 * m + 4 * b + 64, int(1.25 * st['out_h'].numel()) if st else 0)
             st = {
                 'wave_h': torch.empty(cap_w, dtype=torch.float32).pin_memory(),
                 'wave_d': torch.empty(cap_w, dtype=torch.float32, device=self.device),
@@ -286,58 +286,109 @@ class Engine:
             self._stage = st
         return st
 
+    # number of pipeline chunks a large batch is split into so that host staging + H2D of chunk c+1 overlap the
+    # kernels of chunk c (each chunk keeps >= MIN_CHUNK_FRAMES rows so the GEMM / attention grids stay full)
+    MAX_CHUNKS = 4
+    MIN_CHUNK_FRAMES = 32768
+
+    def _chunks(self, cu: np.ndarray) -> List[tuple]:
+        b, m = len(cu) - 1, int(cu[-1])
+        n = int(max(1, min(self.MAX_CHUNKS, b, m // self.MIN_CHUNK_FRAMES)))
+        bounds = [0]
+        for c in range(1, n):
+            target = m * c / n
+            i = int(np.searchsorted(cu, target, side='left'))
+            bounds.append(min(max(i, bounds[-1] + 1), b - (n - c)))
+        bounds.append(b)
+        return [(bounds[i], bounds[i + 1]) for i in range(n)]
+
+    def _pool(self):
+        if getattr(self, '_tp', None) is None:
+            import concurrent.futures
+            import os
+            self._tp = concurrent.futures.ThreadPoolExecutor(max_workers=min(8, max(2, (os.cpu_count() or 4) // 2)))
+        return self._tp
+
     def infer(self, waveforms: Sequence[np.ndarray], quantized: bool = False,
               return_intermediates: bool = False) -> List[Dict[str, np.ndarray]]:
         """waveform-in -> notes-out for a list of clips: the batched equivalent of BaseInference.infer
-        (base_infer.py:46-53).  Host buffers in, host buffers out: every clip is staged through pinned memory
-        and copied H2D asynchronously while the next one is being staged; the notes of the whole batch come
-        back in ONE packed D2H copy [counts | dur | midi | rest]."""
+        (base_infer.py:46-53).  Host buffers in, host buffers out.  The batch is cut into up to 4 chunks of whole
+        clips; for each chunk the clips are staged into pinned memory by a small thread pool (memcpy releases the
+        GIL), copied H2D on a copy stream, and the kernels of the chunk are enqueued behind an event — so staging and
+        H2D of chunk c+1 overlap the kernels of chunk c.  The notes of each chunk come back in ONE packed D2H copy
+        [counts | dur | midi | rest]; there is a single host synchronisation at the end."""
         b = len(waveforms)
         if b == 0:
             return []
         starts, lens, cu, total = self.tables([int(w.shape[0]) for w in waveforms])
-        m, max_frames = int(cu[-1]), int(np.diff(cu).max())
+        m = int(cu[-1])
         dev = self.device
+        chunks = self._chunks(cu) if not return_intermediates else [(0, b)]
         with torch.cuda.device(dev):
             st = self._staging(total, b, m)
             stream = torch.cuda.current_stream(dev)
-            wave_h, wave_d = st['wave_h'], st['wave_d']
-            for s, w, n in zip(starts, waveforms, lens):
-                if n == 0:
-                    continue
-                src = torch.from_numpy(w if (w.dtype == np.float32 and w.flags.c_contiguous)
-                                       else np.ascontiguousarray(w, dtype=np.float32))
-                wave_h[s:s + n].copy_(src)                                      # multi-threaded host memcpy
-                wave_d[s:s + n].copy_(wave_h[s:s + n], non_blocking=True)       # async DMA overlaps the next memcpy
-            tab_h = st['tab_h']
-            tab_h[:b] = torch.from_numpy(starts)
-            tab_h[b:2 * b] = torch.from_numpy(lens)
-            tab_h[2 * b:3 * b + 1] = torch.from_numpy(cu.astype(np.int64))
-            st['tab_d'][:3 * b + 1].copy_(tab_h[:3 * b + 1], non_blocking=True)
-            cu_d = st['tab_d'][2 * b:3 * b + 1].to(torch.int32)
-            ws = self.workspace(m)
-            # decode writes straight into the packed D2H slab: [counts i32 [b] | dur i32 [m] | midi f32 [m] | rest u8 [m]]
-            out_d = st['out_d']
-            note_count = out_d[:4 * b].view(torch.int32)
-            note_dur = out_d[4 * b:4 * b + 4 * m].view(torch.int32)
-            note_midi = out_d[4 * b + 4 * m:4 * b + 8 * m].view(torch.float32)
-            note_rest = out_d[4 * b + 8 * m:4 * b + 9 * m]
-            mel_f32 = torch.empty((m, 80), dtype=torch.float32, device=dev) if return_intermediates else None
-            self.run_mel(wave_d, st['tab_d'][:b], st['tab_d'][b:2 * b], cu_d, b, max_frames, mel_f32, ws.units)
-            self.run_trunk(ws, m, b, cu_d, max_frames, 'softmax' if quantized else 'sigmoid')
-            self.run_decode(ws, m, b, cu_d, note_count, quantized, out=(note_midi, note_dur, note_rest))
-            nbytes = 4 * b + 9 * m
-            st['out_h'][:nbytes].copy_(out_d[:nbytes], non_blocking=True)
+            if getattr(self, '_copy_stream', None) is None:
+                self._copy_stream = torch.cuda.Stream(dev)
+            copy_stream = self._copy_stream
+            copy_stream.wait_stream(stream)       # previous users of the staging / device buffers are done
+            wave_h, wave_d, tab_h, tab_d, out_h, out_d = (st[k] for k in ('wave_h', 'wave_d', 'tab_h', 'tab_d', 'out_h', 'out_d'))
+            hv = wave_h.numpy()
+            pool = self._pool()
+
+            def stage(i):
+                n = int(lens[i])
+                if n:
+                    hv[starts[i]:starts[i] + n] = waveforms[i]          # dtype cast (if any) + memcpy, GIL released
+
+            ws = self.workspace(max(int(cu[c1] - cu[c0]) for c0, c1 in chunks))
             extra = None
-            if return_intermediates:
-                extra = (mel_f32.cpu(), ws.probs[:m].cpu(), ws.bounds[:m].cpu())
+            out_off = 0
+            layout = []
+            for c0, c1 in chunks:
+                bc, mc = c1 - c0, int(cu[c1] - cu[c0])
+                list(pool.map(stage, range(c0, c1)))
+                lo = int(starts[c0])
+                hi = int(starts[c1 - 1] + ((lens[c1 - 1] + 3) & ~3))
+                # var-len tables of this chunk, relative to its own first sample / first frame
+                tab = tab_h[4 * c0:4 * c0 + 3 * bc + 1]
+                tab[:bc] = torch.from_numpy(starts[c0:c1] - lo)
+                tab[bc:2 * bc] = torch.from_numpy(lens[c0:c1])
+                tab[2 * bc:3 * bc + 1] = torch.from_numpy((cu[c0:c1 + 1] - cu[c0]).astype(np.int64))
+                tab_dev = tab_d[4 * c0:4 * c0 + 3 * bc + 1]
+                with torch.cuda.stream(copy_stream):
+                    if hi > lo:
+                        wave_d[lo:hi].copy_(wave_h[lo:hi], non_blocking=True)
+                    tab_dev.copy_(tab, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                stream.wait_event(ev)
+                cu_d = tab_dev[2 * bc:3 * bc + 1].to(torch.int32)
+                max_frames = int(np.diff(cu[c0:c1 + 1]).max())
+                # decode writes straight into this chunk's slab: [counts i32 [bc] | dur i32 [mc] | midi f32 [mc] | rest u8 [mc]]
+                nbytes = 4 * bc + 9 * mc
+                o = out_d[out_off:out_off + nbytes]
+                note_count = o[:4 * bc].view(torch.int32)
+                note_dur = o[4 * bc:4 * bc + 4 * mc].view(torch.int32)
+                note_midi = o[4 * bc + 4 * mc:4 * bc + 8 * mc].view(torch.float32)
+                note_rest = o[4 * bc + 8 * mc:nbytes]
+                mel_f32 = torch.empty((mc, 80), dtype=torch.float32, device=dev) if return_intermediates else None
+                self.run_mel(wave_d[lo:], tab_dev[:bc], tab_dev[bc:2 * bc], cu_d, bc, max_frames, mel_f32, ws.units)
+                self.run_trunk(ws, mc, bc, cu_d, max_frames, 'softmax' if quantized else 'sigmoid')
+                self.run_decode(ws, mc, bc, cu_d, note_count, quantized, out=(note_midi, note_dur, note_rest))
+                out_h[out_off:out_off + nbytes].copy_(o, non_blocking=True)
+                if return_intermediates:
+                    extra = (mel_f32.cpu(), ws.probs[:mc].cpu(), ws.bounds[:mc].cpu())
+                layout.append((c0, c1, out_off, bc, mc))
+                out_off += (nbytes + 15) & ~15
             stream.synchronize()
-            host = st['out_h'][:nbytes].numpy()
-            nc = host[:4 * b].view(np.int32)
-            nd = host[4 * b:4 * b + 4 * m].view(np.int32)
-            nm = host[4 * b + 4 * m:4 * b + 8 * m].view(np.float32)
-            nr = host[4 * b + 8 * m:4 * b + 9 * m]
-            return self.unpack(cu, nc, nm, nd, nr, extra)
+            results: List[Dict[str, np.ndarray]] = []
+            for c0, c1, off, bc, mc in layout:
+                host = out_h[off:off + 4 * bc + 9 * mc].numpy()
+                results.extend(self.unpack(cu[c0:c1 + 1] - cu[c0], host[:4 * bc].view(np.int32),
+                                           host[4 * bc + 4 * mc:4 * bc + 8 * mc].view(np.float32),
+                                           host[4 * bc:4 * bc + 4 * mc].view(np.int32),
+                                           host[4 * bc + 8 * mc:4 * bc + 9 * mc], extra))
+            return results
 
     def unpack(self, cu, nc, nm, nd, nr, extra=None) -> List[Dict[str, np.ndarray]]:
         out = []

@@ -210,6 +210,36 @@ def test_attention_varlen(lib, frames, impl):
             r0 += t
 
 
+def test_attention_growing_max_forces_rescale(lib):
+    """Scores whose row maximum jumps by far more than 2^8 from one key tile to the next: exercises the lazy
+    O-rescale path of the tcgen05 kernel on every tile (a race there shows up as wrong rows)."""
+    torch.manual_seed(8)
+    frames = [1500, 333]
+    cu = _cu(frames)
+    m = int(cu[-1])
+    qkv = torch.randn(m, 1536, device=DEV) * 0.5
+    ramp = torch.cat([torch.arange(t, device=DEV, dtype=torch.float32) / 64.0 for t in frames])   # grows with the key index
+    qkv[:, 512:1024] += ramp[:, None] * torch.sign(torch.randn(1, 512, device=DEV))
+    qkv[:, :512] = qkv[:, :512].abs() * torch.sign(qkv[0:1, 512:1024] - 0.0 + 1e-3) * 2.0
+    qkv = qkv.to(torch.bfloat16)
+    out = torch.full((m, 512), float('nan'), device=DEV, dtype=torch.bfloat16)
+    a = _lib.AttnArgs()
+    a.qkv, a.out = _lib.pair(qkv), _lib.pair(out)
+    a.groups, a.B, a.M, a.cu_frames, a.max_frames = 1, len(frames), m, cu.data_ptr(), max(frames)
+    for _ in range(3):      # repeat: the failure mode is timing dependent
+        out.fill_(float('nan'))
+        _lib.check(lib.some_attention_varlen(C.byref(a), stream()))
+        torch.cuda.synchronize()
+        r0 = 0
+        for t in frames:
+            z = qkv[r0:r0 + t].float()
+            q, k, v = (z[:, j * 512:(j + 1) * 512].reshape(t, 8, 64).transpose(0, 1) for j in range(3))
+            ref = torch.nn.functional.scaled_dot_product_attention(q[None], k[None], v[None])[0]
+            ref = ref.transpose(0, 1).reshape(t, 512)
+            torch.testing.assert_close(out[r0:r0 + t].float(), ref, atol=3e-2, rtol=3e-2)
+            r0 += t
+
+
 def test_mel_matches_torch_stft(lib):
     from some_b200 import synth
     from some_b200.engine import Engine

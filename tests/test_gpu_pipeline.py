@@ -91,6 +91,19 @@ def test_batched_equals_per_clip(tmp_path):
             np.testing.assert_array_equal(rb[k], single[k])
 
 
+def test_chunked_pipeline_equals_single_chunk(tmp_path):
+    """infer() cuts big batches into pipeline chunks (staging / H2D overlap); results must not depend on it."""
+    ins, _ = _plugin('two_head', tmp_path)
+    waves = [synth.synth_waveform(500 + i, seconds=s) for i, s in enumerate([1.3, 0.7, 2.2, 0.4, 1.9, 1.1, 0.9])]
+    whole = ins.infer(waves)
+    ins.model.MIN_CHUNK_FRAMES = 64           # force 4 chunks
+    assert len(ins.model._chunks(np.cumsum([0] + [synth.frames_of(len(w)) for w in waves]).astype(np.int32))) == 4
+    chunked = ins.infer(waves)
+    for a, b in zip(whole, chunked):
+        for k in ('note_midi', 'note_dur', 'note_rest'):
+            np.testing.assert_array_equal(a[k], b[k])
+
+
 def test_silence_is_log_clamp(tmp_path):
     ins, _ = _plugin('two_head', tmp_path)
     units = ins.preprocess(np.zeros(44100, dtype=np.float32))['units']
