@@ -196,7 +196,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     launches0 = eng.launches
-    eng.start_profile()
+    eng.start_profile(cu)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()

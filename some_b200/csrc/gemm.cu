@@ -327,6 +327,333 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Staged epilogue of the trunk GEMMs.  tcgen05.ld hands every thread ONE ROW of the accumulator, so storing (or
+// reading the residual) straight from that mapping makes each 16-byte access of a warp hit 32 different rows:
+// 32 LSU wavefronts per instruction, which made the epilogue as slow as a K = 512 mainloop
+// (profiles/r01_gemm_epilogue_lsu.txt).  Instead each epilogue warp transposes through a private 32 x 128-byte
+// shared-memory tile (16-byte chunks XOR-swizzled with the row, conflict-free both ways) and then moves it with
+// fully coalesced 128-byte rows: lane -> (row = 4 it + lane / 8, 16-byte chunk = lane % 8).
+__device__ __forceinline__ uint32_t stage_off(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
+
+template <bool kResid>
+__device__ __forceinline__ void stage_flush(const GemmParams& p, const GemmGroup& g, int row_base, int lane,
+                                            const uint8_t* stage, size_t col_byte, int elem_bytes, const float4 (&rp)[8]) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = it * 4 + (lane >> 3), ch = lane & 7;
+    float4 v = *reinterpret_cast<const float4*>(stage + stage_off(row, ch));
+    if (row_base + row < p.M) {
+      if constexpr (kResid) v = make_float4(v.x + rp[it].x, v.y + rp[it].y, v.z + rp[it].z, v.w + rp[it].w);
+      uint8_t* dst = static_cast<uint8_t*>(g.out) + (size_t)(row_base + row) * p.ld_out * elem_bytes + col_byte + ch * 16;
+      *reinterpret_cast<float4*>(dst) = v;
+    }
+  }
+}
+__device__ __forceinline__ void resid_prefetch(const GemmParams& p, const GemmGroup& g, int row_base, int lane,
+                                               size_t col_byte, float4 (&rp)[8]) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = it * 4 + (lane >> 3), ch = lane & 7;
+    rp[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row_base + row < p.M)
+      rp[it] = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(g.resid) +
+                                                (size_t)(row_base + row) * p.ld_out * 4 + col_byte + ch * 16);
+  }
+}
+__device__ __forceinline__ void add_bias32(const float* bias, int col, float (&v)[32]) {
+  if (bias == nullptr) return;
+  const float4* b4 = reinterpret_cast<const float4*>(bias + col);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 b = __ldg(b4 + i);
+    v[4 * i + 0] += b.x, v[4 * i + 1] += b.y, v[4 * i + 2] += b.z, v[4 * i + 3] += b.w;
+  }
+}
+
+// One epilogue warp: rows [row_base, +32) x accumulator columns [col0, col0 + 128) of the tile (col_tile = first packed
+// column of the tile).  t_row = TMEM address of the warp's lane quadrant in the current accumulator stage.
+template <int EPI>
+__device__ __forceinline__ void epilogue_warp_staged(const GemmParams& p, const GemmGroup& g, int row_base, int lane,
+                                                     uint32_t t_row, int col0, int col_tile, uint8_t* stage) {
+  const int r = lane;  // row inside the warp's 32-row slab == TMEM lane offset
+  float4 rp[8];
+  if constexpr (EPI == SOME_EPI_STORE_BF16 || EPI == SOME_EPI_SILU_BF16) {
+#pragma unroll 1
+    for (int sc = 0; sc < 2; ++sc) {  // 64 accumulator columns -> 64 bf16 = one 128-byte staged row
+      const int c = col0 + sc * 64;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t acc[32];
+        tmem_ld_32x32(t_row + c + hf * 32, acc);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+        add_bias32(g.bias, col_tile + c + hf * 32, v);
+        if constexpr (EPI == SOME_EPI_SILU_BF16) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = silu_fast(v[i]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(stage + stage_off(r, hf * 4 + q)) =
+              make_uint4(pack_bf16x2(v[8 * q + 0], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                         pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+      }
+      __syncwarp();
+      stage_flush<false>(p, g, row_base, lane, stage, (size_t)(col_tile + c) * 2, 2, rp);
+      __syncwarp();
+    }
+  } else if constexpr (EPI == SOME_EPI_GLU_BF16) {
+    // 128 packed columns (4 x [16 out | 16 gate]) -> 64 bf16 outputs = one staged row
+#pragma unroll
+    for (int sub = 0; sub < 4; ++sub) {
+      uint32_t acc[32];
+      tmem_ld_32x32(t_row + col0 + sub * 32, acc);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+      add_bias32(g.bias, col_tile + col0 + sub * 32, v);
+      float o[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] = v[i] * sigmoid_fast(v[16 + i]);
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+        *reinterpret_cast<uint4*>(stage + stage_off(r, sub * 2 + q)) =
+            make_uint4(pack_bf16x2(o[8 * q + 0], o[8 * q + 1]), pack_bf16x2(o[8 * q + 2], o[8 * q + 3]),
+                       pack_bf16x2(o[8 * q + 4], o[8 * q + 5]), pack_bf16x2(o[8 * q + 6], o[8 * q + 7]));
+    }
+    __syncwarp();
+    stage_flush<false>(p, g, row_base, lane, stage, (size_t)((col_tile + col0) >> 1) * 2, 2, rp);
+    __syncwarp();
+  } else if constexpr (EPI == SOME_EPI_RESID_F32) {
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {  // 32 accumulator columns -> 32 f32 = one staged row
+      const int c = col0 + ch * 32;
+      resid_prefetch(p, g, row_base, lane, (size_t)(col_tile + c) * 4, rp);  // coalesced, in flight during the math
+      uint32_t acc[32];
+      tmem_ld_32x32(t_row + c, acc);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+      add_bias32(g.bias, col_tile + c, v);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(stage + stage_off(r, q)) =
+            make_float4(p.alpha * v[4 * q], p.alpha * v[4 * q + 1], p.alpha * v[4 * q + 2], p.alpha * v[4 * q + 3]);
+      __syncwarp();
+      stage_flush<true>(p, g, row_base, lane, stage, (size_t)(col_tile + c) * 4, 4, rp);
+      __syncwarp();
+    }
+  } else if constexpr (EPI == SOME_EPI_GLU_RESID_F32) {
+#pragma unroll 1
+    for (int sc = 0; sc < 2; ++sc) {  // 64 packed columns -> 32 f32 outputs = one staged row
+      const int c = col0 + sc * 64;
+      const size_t out_byte = (size_t)((col_tile + c) >> 1) * 4;
+      resid_prefetch(p, g, row_base, lane, out_byte, rp);
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        uint32_t acc[32];
+        tmem_ld_32x32(t_row + c + sub * 32, acc);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+        add_bias32(g.bias, col_tile + c + sub * 32, v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(stage + stage_off(r, sub * 4 + q)) =
+              make_float4(v[4 * q] * sigmoid_fast(v[16 + 4 * q]), v[4 * q + 1] * sigmoid_fast(v[16 + 4 * q + 1]),
+                          v[4 * q + 2] * sigmoid_fast(v[16 + 4 * q + 2]), v[4 * q + 3] * sigmoid_fast(v[16 + 4 * q + 3]));
+      }
+      __syncwarp();
+      stage_flush<true>(p, g, row_base, lane, stage, out_byte, 4, rp);
+      __syncwarp();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs computes a 256 x 256 tile with M = 256 MMAs.  Each CTA
+// loads its own 128 rows of A and only HALF of the W tile (128 rows), so the L2 -> SM traffic per MAC drops
+// from (128 + 256) / (128 * 256) to (128 + 128) / (128 * 256) operand rows: the single-CTA kernel is capped by
+// the ~6300 B/clk L2 -> SM fabric at ~45 % of the tensor peak (profiles/r01_gemm_ncu_full_summary.csv).
+//   producer (warp 0, both CTAs): TMA with .cta_group::2, completion bytes land on the LEADER's full barrier
+//   MMA (warp 1, leader only): tcgen05.mma.cta_group::2 M256 N256 K16; commits are multicast to both CTAs
+//   epilogue (warps 4-11, both CTAs): own 128 TMEM lanes; tmem_empty arrivals go to the leader (remote arrive)
+constexpr int PAIR_STAGES = 5;
+constexpr int PAIR_BN = 256;
+constexpr int PAIR_STAGE_BYTES = BLOCK_M * BLOCK_K * 2 + (PAIR_BN / 2) * BLOCK_K * 2;  // 16 KB A + 16 KB half W
+constexpr int PAIR_EPI_BYTES = EPI_WARPS * 4096;  // one 32 x 128 B transposition tile per epilogue warp
+constexpr int PAIR_SMEM = PAIR_STAGES * PAIR_STAGE_BYTES + PAIR_EPI_BYTES + 1024 + 256;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+                 const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* epi_stage = smem + PAIR_STAGES * PAIR_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + PAIR_EPI_BYTES);
+  uint64_t* full_bar = bars;                               // [STAGES]  (used in the leader)
+  uint64_t* empty_bar = bars + PAIR_STAGES;                // [STAGES]  (local, multicast commit)
+  uint64_t* tmem_full = bars + 2 * PAIR_STAGES;            // [2]       (local, multicast commit)
+  uint64_t* tmem_empty = bars + 2 * PAIR_STAGES + 2;       // [2]       (used in the leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * PAIR_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  const int num_m = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int num_n = p.N / PAIR_BN;
+  const int tiles_per_group = num_m * num_n;
+  const int num_tiles = tiles_per_group * p.groups;
+  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (p.groups > 1) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmB1);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < PAIR_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);   // the leader's producer arrives and expects the bytes of BOTH CTAs
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_pair<512>(tmem_slot);
+  tc_fence_before_sync();
+  cluster_sync_all();   // barrier inits + TMEM allocation of BOTH CTAs visible before any remote arrive / multicast
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int grp = tile / tiles_per_group;
+        const int t = tile - grp * tiles_per_group;
+        const int m_blk = t / num_n, n_blk = t - m_blk * num_n;
+        const CUtensorMap* ta = grp == 0 ? &tmA0 : &tmA1;
+        const CUtensorMap* tb = grp == 0 ? &tmB0 : &tmB1;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          // The follower never arrives: its bytes may land before the leader's expect_tx (the transaction count goes
+          // negative transiently) but the phase cannot complete until the leader has arrived and all bytes are in.
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * PAIR_STAGE_BYTES);
+          uint8_t* sa = smem + stage * PAIR_STAGE_BYTES;
+          tma_load_2d_pair(sa, ta, full_leader, kb * BLOCK_K, m_blk * 2 * BLOCK_M + rank * BLOCK_M);
+          tma_load_2d_pair(sa + BLOCK_M * BLOCK_K * 2, tb, full_leader, kb * BLOCK_K, n_blk * PAIR_BN + rank * (PAIR_BN / 2));
+          if (++stage == PAIR_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(2 * BLOCK_M, PAIR_BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * PAIR_BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(smem + stage * PAIR_STAGE_BYTES);
+          const uint64_t adesc = umma_desc_kmajor_sw128(sa);
+          const uint64_t bdesc = umma_desc_kmajor_sw128(sa + BLOCK_M * BLOCK_K * 2);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_pair(&empty_bar[stage], 0b11);   // both CTAs' producers may refill this slot
+          if (++stage == PAIR_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_pair(&tmem_full[acc], 0b11);        // both CTAs' epilogues may read their accumulator half
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int quad = warp & 3;
+    const int half = ew >> 2;
+    constexpr int COLS_PER_WARP = PAIR_BN / 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int grp = tile / tiles_per_group;
+      const int t = tile - grp * tiles_per_group;
+      const int m_blk = t / num_n, n_blk = t - m_blk * num_n;
+      const GemmGroup& g = p.g[grp];
+      const int row_base = m_blk * 2 * BLOCK_M + rank * BLOCK_M + quad * 32;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t t_row = tmem_base + acc * PAIR_BN + (static_cast<uint32_t>(quad * 32) << 16);
+      epilogue_warp_staged<EPI>(p, g, row_base, lane, t_row, half * COLS_PER_WARP, n_blk * PAIR_BN, epi_stage + ew * 4096);
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  cluster_sync_all();   // no CTA of the pair may free TMEM / exit while its peer still uses it
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc_pair<512>(tmem_base);
+  }
+}
+
+template <int EPI>
+static int launch_gemm_pair(const CUtensorMap* maps, const GemmParams& p, cudaStream_t stream) {
+  auto kern = gemm_pair_kernel<EPI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM);
+    SOME_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(gemm_pair, %d B smem): %s", PAIR_SMEM, cudaGetErrorString(e));
+    configured = true;
+  }
+  const int num_m = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int tiles = num_m * (p.N / PAIR_BN) * p.groups;
+  int pairs = num_sms() / 2;
+  if (tiles < pairs) pairs = tiles;
+  kern<<<2 * pairs, GEMM_THREADS, PAIR_SMEM, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+  return check_launch("some_gemm(pair)");
+}
+
 template <int BLOCK_N, int EPI>
 static int launch_gemm(const CUtensorMap* maps, const GemmParams& p, cudaStream_t stream) {
   using S = GemmSmem<BLOCK_N>;
@@ -368,12 +695,13 @@ extern "C" int some_gemm(const some_gemm_args* a, cudaStream_t stream) {
   p.ld_out = a->ld_out;
   p.n_valid = a->N;
   p.alpha = a->alpha;
+  const bool use_pair = !head;   // 256 x 256 CTA-pair tiles for every trunk GEMM; heads / input projection stay 1-CTA
   CUtensorMap maps[4];
   for (int g = 0; g < 2; ++g) {
     const int s = g < a->groups ? g : 0;
     SOME_REQUIRE(a->A[s] != nullptr && a->W[s] != nullptr && a->out[s] != nullptr, "some_gemm: null pointer in group %d", s);
     if (make_tmap_bf16_2d(&maps[2 * g], a->A[s], a->M, a->K, a->lda, BLOCK_M)) return -1;
-    if (make_tmap_bf16_2d(&maps[2 * g + 1], a->W[s], a->N, a->K, a->K, 256)) return -1;
+    if (make_tmap_bf16_2d(&maps[2 * g + 1], a->W[s], a->N, a->K, a->K, use_pair ? 128 : 256)) return -1;
     p.g[g].bias = a->bias[s];
     p.g[g].out = a->out[s];
     p.g[g].resid = a->resid[s];
@@ -381,11 +709,11 @@ extern "C" int some_gemm(const some_gemm_args* a, cudaStream_t stream) {
   const bool needs_resid = (epi == SOME_EPI_RESID_F32 || epi == SOME_EPI_GLU_RESID_F32);
   if (needs_resid) SOME_REQUIRE(a->resid[0] != nullptr, "some_gemm: epilogue %d needs a residual pointer", epi);
   switch (epi) {
-    case SOME_EPI_STORE_BF16: return launch_gemm<256, SOME_EPI_STORE_BF16>(maps, p, stream);
-    case SOME_EPI_SILU_BF16: return launch_gemm<256, SOME_EPI_SILU_BF16>(maps, p, stream);
-    case SOME_EPI_GLU_BF16: return launch_gemm<256, SOME_EPI_GLU_BF16>(maps, p, stream);
-    case SOME_EPI_RESID_F32: return launch_gemm<256, SOME_EPI_RESID_F32>(maps, p, stream);
-    case SOME_EPI_GLU_RESID_F32: return launch_gemm<256, SOME_EPI_GLU_RESID_F32>(maps, p, stream);
+    case SOME_EPI_STORE_BF16: return launch_gemm_pair<SOME_EPI_STORE_BF16>(maps, p, stream);
+    case SOME_EPI_SILU_BF16: return launch_gemm_pair<SOME_EPI_SILU_BF16>(maps, p, stream);
+    case SOME_EPI_GLU_BF16: return launch_gemm_pair<SOME_EPI_GLU_BF16>(maps, p, stream);
+    case SOME_EPI_RESID_F32: return launch_gemm_pair<SOME_EPI_RESID_F32>(maps, p, stream);
+    case SOME_EPI_GLU_RESID_F32: return launch_gemm_pair<SOME_EPI_GLU_RESID_F32>(maps, p, stream);
     case SOME_EPI_BIAS_F32: return launch_gemm<256, SOME_EPI_BIAS_F32>(maps, p, stream);
     case SOME_EPI_SIGMOID_F32: return launch_gemm<256, SOME_EPI_SIGMOID_F32>(maps, p, stream);
     case SOME_EPI_SOFTMAX_F32: return launch_gemm<256, SOME_EPI_SOFTMAX_F32>(maps, p, stream);

@@ -61,12 +61,16 @@ class Engine:
         self.timestep = config['hop_size'] / config['audio_sample_rate']
         self._ws: Optional[_Workspace] = None
         self.launches = 0
+        self._sum_t2 = 0.0
         # optional per-kernel timing: name -> [(start_event, end_event, work)] where work = FLOPs (GEMM,
         # attention) or algorithmic bytes (HBM-bound kernels); enabled by bench.py via start_profile()
         self.prof: Optional[dict] = None
 
-    def start_profile(self):
+    def start_profile(self, cu_frames_host=None):
         self.prof = {}
+        if cu_frames_host is not None:
+            t = np.diff(np.asarray(cu_frames_host)).astype(np.float64)
+            self._sum_t2 = float((t * t).sum())
 
     def stop_profile(self) -> Dict[str, dict]:
         """Returns {kernel: {launches, ms, work}} from the CUDA events recorded since start_profile()."""
@@ -203,11 +207,9 @@ class Engine:
         (Gmidi_conform.py:30-40).  Reads ws.units; writes ws.probs [m, outdim] and ws.bounds [m].
         head: 'sigmoid' | 'softmax' | 'logits'."""
         w, x, a = self.w, ws.x, ws.a
-        if self.prof is not None:   # QK^T + PV MACs of one attention launch (both streams): 2 * 8 * 64 * sum T^2
-            t = torch.diff(cu_frames).double()
-            self._att_flops = float(2 * 2 * 512 * (t * t).sum().item())
-        else:
-            self._att_flops = 0.0
+        # QK^T + PV MACs of one attention launch (both streams): 2 * 8 heads * 64 * sum T^2 (profiling only; the clip
+        # lengths come from the host copy of cu_frames so that no device sync sneaks into the timed region)
+        self._att_flops = float(2 * 2 * 512 * self._sum_t2) if self.prof is not None else 0.0
         self._gemm(ws.units, ws.units, w.w_in[0], w.w_in[1], w.b_in[0], w.b_in[1], x[0], x[1], None, None,
                    m, DIM, 80, 80, DIM, _lib.EPI_BIAS_F32)                       # inln / inln1
         for i in range(w.lay):
