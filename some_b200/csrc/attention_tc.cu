@@ -7,7 +7,7 @@
 //
 // CTA = 128 query rows of one (clip, head), 64-key tiles; 2 CTAs per SM (96 KB smem, 256 TMEM columns each).
 // Roles (256 threads):
-//   warp 0   TMA producer: Q once, then (K_j, V_j) 64-key tiles into a 3-stage ring (128-B swizzle)
+//   warp 0   TMA producer: Q once, then (K_j, V_j) 64-key tiles into a 4-stage ring (128-B swizzle)
 //   warp 1   MMA issuer (one thread):  S_j = Q K_j^T  (tcgen05.mma M128 N64 K16 x4, both operands K-major) into one of
 //            TWO S buffers, so QK_{j+2} is issued as soon as the softmax has consumed S_j and the softmax never waits
 //            for the tensor core in steady state;  O += P_j V_j  (M128 N64 K16 x4, A = P from smem, B = V MN-major)
@@ -28,7 +28,7 @@ constexpr int TC_BM = 128;                 // queries per CTA
 constexpr int TC_BN = 64;                  // keys per tile
 constexpr int TC_QTILE = 128 * 64 * 2;     // 16 KB
 constexpr int TC_KTILE = TC_BN * 64 * 2;   // 8 KB (K or V tile)
-constexpr int TC_STAGES = 3;
+constexpr int TC_STAGES = 4;  // K/V tile j+3 is requested when PV_{j-1} retires: two tile periods to cover the TMA latency
 constexpr int TC_PTILE = 128 * TC_BN * 2;  // 16 KB
 constexpr int TC_SMEM = TC_QTILE + TC_STAGES * 2 * TC_KTILE + 2 * TC_PTILE + 128 /*barriers*/;
 constexpr uint32_t TC_TMEM_COLS = 256;
@@ -56,12 +56,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
   uint8_t* sP = sKV + TC_STAGES * 2 * TC_KTILE;                    // two P buffers, one 64-key K-major atom each
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * TC_PTILE);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;    // [3]
-  uint64_t* kv_empty = bars + 4;   // [3]
-  uint64_t* s_full = bars + 7;     // [2]
-  uint64_t* p_full = bars + 9;     // [2]
-  uint64_t* pv_done = bars + 11;   // [2], alternating by tile parity
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* kv_full = bars + 1;    // [4]
+  uint64_t* kv_empty = bars + 5;   // [4]
+  uint64_t* s_full = bars + 9;     // [2]
+  uint64_t* p_full = bars + 11;    // [2]
+  uint64_t* pv_done = bars + 13;   // [2], alternating by tile parity
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int clip = blockIdx.x / p.tiles_per_clip;

@@ -39,6 +39,12 @@ __device__ __forceinline__ int rev4_10(int k) {
   return ((b & 0x2AA) >> 1) | ((b & 0x155) << 1);        // swap the bits inside each digit back
 }
 
+// Shared-memory index swizzle of the 1024-point work buffer (float2 elements, 16 per 128-byte bank row): the low four
+// index bits are XORed with bits 4-5 (twice) and bits 6-9, which keeps every access pattern of the kernel conflict-free:
+// the strided butterflies of the last two radix-4 stages (threads differ in bits 2-5) and the digit-reversed reads of
+// the real-FFT unpack (consecutive bins differ only in bits 6-9).
+__device__ __forceinline__ int zsw(int i) { return i ^ (((i >> 4) & 3) * 5) ^ ((i >> 6) & 15); }
+
 __global__ void __launch_bounds__(256)
 mel_kernel(const float* __restrict__ wave, const int64_t* __restrict__ clip_start, const int64_t* __restrict__ clip_len,
            const int32_t* __restrict__ cu_frames,
@@ -97,7 +103,7 @@ mel_kernel(const float* __restrict__ wave, const int64_t* __restrict__ clip_star
       for (int n = tid; n < 1024; n += 128) {
         const float2 xv = *reinterpret_cast<const float2*>(xf + 2 * n);
         const float2 wv = *reinterpret_cast<const float2*>(s_win + 2 * n);
-        z[n] = make_float2(xv.x * wv.x, xv.y * wv.y);
+        z[zsw(n)] = make_float2(xv.x * wv.x, xv.y * wv.y);
       }
     }
     __syncthreads();
@@ -112,7 +118,8 @@ mel_kernel(const float* __restrict__ wave, const int64_t* __restrict__ clip_star
           const int b = tid + 128 * i;
           const int grp = b / q, j = b - grp * q;
           const int base = grp * Lg + j;
-          const float2 a = z[base], bb = z[base + q], c = z[base + 2 * q], d = z[base + 3 * q];
+          const int i0 = zsw(base), i1 = zsw(base + q), i2 = zsw(base + 2 * q), i3 = zsw(base + 3 * q);
+          const float2 a = z[i0], bb = z[i1], c = z[i2], d = z[i3];
           const float2 t0 = make_float2(a.x + c.x, a.y + c.y);
           const float2 t1 = make_float2(a.x - c.x, a.y - c.y);
           const float2 t2 = make_float2(bb.x + d.x, bb.y + d.y);
@@ -127,7 +134,7 @@ mel_kernel(const float* __restrict__ wave, const int64_t* __restrict__ clip_star
             y2 = cmul(y2, tw2048(s_tw, 2 * e));
             y3 = cmul(y3, tw2048(s_tw, 3 * e));
           }
-          z[base] = y0, z[base + q] = y1, z[base + 2 * q] = y2, z[base + 3 * q] = y3;
+          z[i0] = y0, z[i1] = y1, z[i2] = y2, z[i3] = y3;
         }
       }
       __syncthreads();
@@ -136,8 +143,8 @@ mel_kernel(const float* __restrict__ wave, const int64_t* __restrict__ clip_star
     //      O = -i (Z[k] - conj Z[N-k]) / 2
     if (active) {
       for (int k = tid; k < SOME_MEL_BINS; k += 128) {
-        const float2 zk = z[rev4_10(k)];
-        const float2 zn = z[rev4_10((1024 - k) & 1023)];
+        const float2 zk = z[zsw(rev4_10(k))];
+        const float2 zn = z[zsw(rev4_10((1024 - k) & 1023))];
         const float2 E = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
         const float2 dlt = make_float2(zk.x - zn.x, zk.y + zn.y);  // Z[k] - conj(Z[N-k])
         const float2 O = make_float2(0.5f * dlt.y, -0.5f * dlt.x);  // -i/2 * dlt

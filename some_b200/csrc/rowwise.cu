@@ -103,15 +103,18 @@ bound_head_kernel(const float* __restrict__ x, const float* __restrict__ gamma, 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Depthwise conv.  CTA = one 128-frame tile of one clip x 64 channels (grid.x = clip * tiles_per_clip + tile;
-// tiles past the end of a short clip exit at once).  The (128 + 30) x 64 input
-// window is staged in shared memory (zeros outside the clip).  Each thread owns a channel pair and 16
-// consecutive frames: 31 x 2 folded taps and 16 x 2 accumulators live in registers, the 46 input rows
-// stream through once (row-major accumulation, fully unrolled, no per-tap predicates).
+// Depthwise conv.  Work item = one 128-frame tile of one clip x 64 channels (tiles never span clips; frames outside
+// the clip read as zero).  Persistent CTAs: a CTA keeps ONE channel block for its whole life, so the 31 x 2 BN-folded
+// taps of each thread are loaded into registers once, and it walks over frame tiles with a cp.async double buffer
+// (the (128 + 30) x 64 bf16 window of the next tile streams in while the current one is computed).  Each thread owns a
+// channel pair and 16 consecutive frames: 16 packed-f32x2 accumulators, the 46 input rows stream through once
+// (row-major accumulation, fully unrolled, no per-tap predicates).
 constexpr int DW_T = 128;     // frames per tile
 constexpr int DW_C = 64;      // channels per CTA
 constexpr int DW_FR = 16;     // frames per thread
 constexpr int DW_HALO = 15;
+constexpr int DW_ROWS = DW_T + 2 * DW_HALO;
+constexpr int DW_TILE_BYTES = DW_ROWS * DW_C * 2;
 
 struct DwParams {
   const __nv_bfloat16* x[2];
@@ -120,62 +123,85 @@ struct DwParams {
   __nv_bfloat16* out[2];
   const int32_t* cu_frames;
   int tiles_per_clip;
+  int num_tiles;      // tiles_per_clip * B
+  int ctas_per_cb;    // CTAs sharing one (channel block, group)
 };
 
 __global__ void __launch_bounds__(256) dwconv_kernel(const DwParams p) {
-  __shared__ __align__(16) __nv_bfloat16 tile[(DW_T + 2 * DW_HALO) * DW_C];
+  __shared__ __align__(16) __nv_bfloat16 tile[2][DW_ROWS * DW_C];
   const int grp = blockIdx.z;
   const int c0 = blockIdx.y * DW_C;
-  const int clip = blockIdx.x / p.tiles_per_clip;
-  const int tile_in_clip = blockIdx.x - clip * p.tiles_per_clip;
-  const int clip_begin = p.cu_frames[clip], clip_end = p.cu_frames[clip + 1];
-  const int row0 = clip_begin + tile_in_clip * DW_T;
-  if (row0 >= clip_end) return;
   const __nv_bfloat16* __restrict__ x = p.x[grp];
-
-  // stage rows [row0 - 15, row0 + 128 + 15) x 64 channels: 8 x 16-byte chunks per row
-  for (int i = threadIdx.x; i < (DW_T + 2 * DW_HALO) * 8; i += 256) {
-    const int r = i >> 3, ch = i & 7;
-    const int grow = row0 - DW_HALO + r;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (grow >= clip_begin && grow < clip_end)
-      v = *reinterpret_cast<const uint4*>(x + (size_t)grow * D + c0 + ch * 8);
-    *reinterpret_cast<uint4*>(tile + r * DW_C + ch * 8) = v;
-  }
+  __nv_bfloat16* __restrict__ out = p.out[grp];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = c0 + 2 * lane;
-  float w0[SOME_CONV_K], w1[SOME_CONV_K];
+
+  auto tile_rows = [&](int t, int& clip_begin, int& clip_end, int& row0) -> bool {
+    const int clip = t / p.tiles_per_clip;
+    clip_begin = p.cu_frames[clip];
+    clip_end = p.cu_frames[clip + 1];
+    row0 = clip_begin + (t - clip * p.tiles_per_clip) * DW_T;
+    return row0 < clip_end;
+  };
+  auto prefetch = [&](int t, int buf) {  // rows [row0 - 15, row0 + 128 + 15) x 64 channels, 8 x 16 B per row
+    int clip_begin, clip_end, row0;
+    if (!tile_rows(t, clip_begin, clip_end, row0)) return;
+    const uint32_t dst0 = smem_u32(&tile[buf][0]);
+    for (int i = threadIdx.x; i < DW_ROWS * 8; i += 256) {
+      const int r = i >> 3, ch = i & 7;
+      const int grow = row0 - DW_HALO + r;
+      const bool ok = grow >= clip_begin && grow < clip_end;
+      const int sz = ok ? 16 : 0;  // src-size 0 => zero fill (the per-clip zero padding of the conv)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (r * DW_C + ch * 8) * 2),
+                   "l"(x + (size_t)(ok ? grow : clip_begin) * D + c0 + ch * 8), "r"(sz)
+                   : "memory");
+    }
+  };
+
+  // Packed fp32x2 FMAs (sm_100 FFMA2): {a[c], a[c+1]} += {w[c], w[c+1]} * {x[c], x[c+1]} in ONE instruction per lane.
+  uint64_t w[SOME_CONV_K];
 #pragma unroll
-  for (int k = 0; k < SOME_CONV_K; ++k) {
-    const float2 ww = __ldg(reinterpret_cast<const float2*>(p.w[grp] + k * D + c));
-    w0[k] = ww.x, w1[k] = ww.y;
-  }
-  const float2 bb = __ldg(reinterpret_cast<const float2*>(p.b[grp] + c));
-  float a0[DW_FR], a1[DW_FR];
+  for (int k = 0; k < SOME_CONV_K; ++k) w[k] = __ldg(reinterpret_cast<const unsigned long long*>(p.w[grp] + k * D + c));
+  const uint64_t bb = __ldg(reinterpret_cast<const unsigned long long*>(p.b[grp] + c));
+
+  int t = blockIdx.x, buf = 0;
+  if (t < p.num_tiles) prefetch(t, 0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (; t < p.num_tiles; t += p.ctas_per_cb, buf ^= 1) {
+    if (t + p.ctas_per_cb < p.num_tiles) prefetch(t + p.ctas_per_cb, buf ^ 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    int clip_begin, clip_end, row0;
+    if (tile_rows(t, clip_begin, clip_end, row0)) {
+      uint64_t a[DW_FR];
 #pragma unroll
-  for (int f = 0; f < DW_FR; ++f) a0[f] = bb.x, a1[f] = bb.y;
-  __syncthreads();
-  const int f0 = warp * DW_FR;  // first output frame (tile-relative) of this thread
+      for (int f = 0; f < DW_FR; ++f) a[f] = bb;
+      const int f0 = warp * DW_FR;  // first output frame (tile-relative) of this thread
+      const __nv_bfloat16* tb = &tile[buf][0];
 #pragma unroll
-  for (int r = 0; r < DW_FR + SOME_CONV_K - 1; ++r) {
-    const __nv_bfloat162 xv = *reinterpret_cast<const __nv_bfloat162*>(tile + (f0 + r) * DW_C + 2 * lane);
-    const float x0 = __low2float(xv), x1 = __high2float(xv);
+      for (int r = 0; r < DW_FR + SOME_CONV_K - 1; ++r) {
+        const uint32_t xb = *reinterpret_cast<const uint32_t*>(tb + (f0 + r) * DW_C + 2 * lane);  // bf16x2
+        // bf16 -> f32 is a 16-bit shift: {lo, hi} as packed f32x2
+        const uint64_t xv = (static_cast<uint64_t>(xb & 0xffff0000u) << 32) | static_cast<uint64_t>(xb << 16);
 #pragma unroll
-    for (int f = 0; f < DW_FR; ++f) {
-      const int k = r - f;  // tap index: output f reads input rows f .. f + 30 (tile row = frame + 15 - 15 + k)
-      if (k >= 0 && k < SOME_CONV_K) {
-        a0[f] = fmaf(w0[k], x0, a0[f]);
-        a1[f] = fmaf(w1[k], x1, a1[f]);
+        for (int f = 0; f < DW_FR; ++f) {
+          const int k = r - f;  // tap index: output frame f reads tile rows f .. f + 30
+          if (k >= 0 && k < SOME_CONV_K) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a[f]) : "l"(w[k]), "l"(xv));
+        }
+      }
+#pragma unroll
+      for (int f = 0; f < DW_FR; ++f) {
+        const int grow = row0 + f0 + f;
+        if (grow < clip_end) {
+          const float a0 = __uint_as_float(static_cast<uint32_t>(a[f])), a1 = __uint_as_float(static_cast<uint32_t>(a[f] >> 32));
+          *reinterpret_cast<uint32_t*>(out + (size_t)grow * D + c) = pack_bf16x2(silu_fast(a0), silu_fast(a1));
+        }
       }
     }
+    __syncthreads();  // everyone is done with tile[buf] before the prefetch of the iteration after next refills it
   }
-  __nv_bfloat16* __restrict__ out = p.out[grp];
-#pragma unroll
-  for (int f = 0; f < DW_FR; ++f) {
-    const int grow = row0 + f0 + f;
-    if (grow < clip_end)
-      *reinterpret_cast<uint32_t*>(out + (size_t)grow * D + c) = pack_bf16x2(silu_fast(a0[f]), silu_fast(a1[f]));
-  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 }  // namespace some
@@ -222,9 +248,13 @@ extern "C" int some_dwconv_bn_silu(const some_dwconv_args* a, cudaStream_t strea
   }
   p.cu_frames = a->cu_frames;
   p.tiles_per_clip = (a->max_frames + DW_T - 1) / DW_T;
-  const long long gx = 1ll * p.tiles_per_clip * a->B;
-  SOME_REQUIRE(gx < (1ll << 31), "some_dwconv_bn_silu: grid too large");
-  dim3 grid(static_cast<unsigned>(gx), D / DW_C, a->groups);
+  const long long nt = 1ll * p.tiles_per_clip * a->B;
+  SOME_REQUIRE(nt < (1ll << 31), "some_dwconv_bn_silu: too many tiles");
+  p.num_tiles = static_cast<int>(nt);
+  // persistent grid: ~2 CTAs per SM in total, split evenly over the (channel block, group) pairs
+  const int per_cb = (2 * num_sms() + (D / DW_C) * a->groups - 1) / ((D / DW_C) * a->groups);
+  p.ctas_per_cb = static_cast<int>(nt < per_cb ? nt : per_cb);
+  dim3 grid(p.ctas_per_cb, D / DW_C, a->groups);
   dwconv_kernel<<<grid, 256, 0, stream>>>(p);
   return check_launch("some_dwconv_bn_silu");
 }

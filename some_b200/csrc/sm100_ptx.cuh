@@ -28,26 +28,26 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or ~the hint elapses)
+// instead of burning issue slots that the softmax / epilogue warps of the same SM sub-partition need.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(200000u)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a pipeline bug becomes a trap (launch error) after ~4 s instead of a hung GPU.
+// Bounded wait: a pipeline bug becomes a trap (launch error) instead of a hung GPU.  The bound is a retry count, so the
+// steady-state loop is just TRYWAIT + branch (an earlier version read %globaltimer every iteration and the spinning
+// TMA / MMA warps took ~25 % of the issue slots of their sub-partition: profiles/r01_attention_tc_v2_notes.txt).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  uint64_t t0;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    uint64_t t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    if (t1 - t0 > 4000000000ull) {
+    if (++spins == (1u << 24)) {
       printf("some_b200: mbarrier timeout block %d thread %d bar@%u parity %u\n", (int)blockIdx.x, (int)threadIdx.x,
              smem_u32(bar), parity);
       __trap();
