@@ -40,6 +40,7 @@ typedef struct CUstream_st* cudaStream_t;
 #define SOME_HOP 512
 #define SOME_MEL_BINS 372 /* spectrum bins 0..371 carry all non-zero mel weights (fmax = 8 kHz) */
 #define SOME_MEL_MAXW 24  /* widest mel filter, in bins */
+#define SOME_MEL_TW 1392  /* complex twiddles: radix-4 stage tables 3 x (256 + 64 + 16 + 4), then W_2048^k for k < 372 */
 
 int some_version(void);
 const char* some_last_error(void);
@@ -53,7 +54,9 @@ const char* some_last_error(void);
  *   mel_start     int32 [80]: first spectrum bin with non-zero weight in filter m
  *   mel_count     int32 [80]: number of contiguous non-zero bins (<= SOME_MEL_MAXW)
  *   mel_weights   f32 [80][SOME_MEL_MAXW]: those weights (librosa htk / slaney filterbank, spec.py:22-28)
- *   twiddle       f32 [1024][2]: cos / sin(-2 pi j / 2048), j < 1024 (host-computed in double)
+ *   twiddle       f32 [SOME_MEL_TW][2] (cos, sin), host-computed in double: for the radix-4 DIF stages s = 0..3 with
+ *                 L = 1024 / 4^s, q = L / 4: exp(-2 pi i m j / L) for m = 1, 2, 3 and j < q (m-major), then
+ *                 exp(-2 pi i k / 2048) for k < 372 (real-FFT unpack)
  *   window        f32 [2048] periodic Hann (torch.hann_window)
  *   out_f32       f32 [M, 80] or NULL;  out_bf16  bf16 [M, 80] or NULL (A operand of the input projections) */
 int some_mel_logmel(const float* wave, const int64_t* clip_start, const int64_t* clip_len,

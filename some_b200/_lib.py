@@ -13,6 +13,7 @@ EPI_STORE_BF16, EPI_SILU_BF16, EPI_GLU_BF16, EPI_RESID_F32, EPI_GLU_RESID_F32, E
     EPI_SIGMOID_F32, EPI_SOFTMAX_F32 = range(8)
 
 DIM, HEADS, HEAD_DIM, CONV_K, N_MELS, N_FFT, HOP, MEL_BINS, MEL_MAXW = 512, 8, 64, 31, 80, 2048, 512, 372, 24
+MEL_TW = 1392
 
 _vp = C.c_void_p
 

@@ -7,7 +7,7 @@
 //   1. the (16 + 3) x 512 samples the frames overlap are staged once in shared memory with coalesced
 //      float4 loads; samples outside [0, L) read as zero (the reference's F.pad 1024 / 1024);
 //   2. per frame: z[n] = w[2n] x[2n] + i w[2n+1] x[2n+1], in-place radix-4 DIF FFT of 1024 complex points in
-//      shared memory (5 stages, host-computed double-precision twiddles), result in base-4 digit-reversed order;
+//      shared memory (5 stages, host-computed double-precision per-stage twiddle tables), result in base-4 digit-reversed order;
 //   3. real-FFT unpack for bins 0..371 only (mel weights above 8 kHz are zero), |X|;
 //   4. mel[m] = sum over the filter's contiguous bin range (<= 24 bins), log(max(., clamp)).
 // Algorithmic traffic: 512 x 4 B in + 80 x 4 B out per frame (2368 B); the FFT itself (~56 kFLOP/frame fp32,
@@ -22,16 +22,12 @@ namespace some {
 constexpr int MEL_FPB = 16;                    // frames per CTA
 constexpr int MEL_NS = (MEL_FPB + 3) * 512;    // staged samples
 constexpr int MEL_MAXW = SOME_MEL_MAXW;
-constexpr int MEL_SMEM = MEL_NS * 4 + 1024 * 8 /*twiddle*/ + 2048 * 4 /*window*/ + 2 * 1024 * 8 /*work*/ +
+constexpr int MEL_TW = SOME_MEL_TW;             // per-stage twiddles (3 x 256 | 3 x 64 | 3 x 16 | 3 x 4) + 372 unpack
+constexpr int MEL_SMEM = MEL_NS * 4 + MEL_TW * 8 /*twiddle*/ + 2048 * 4 /*window*/ + 2 * 1024 * 8 /*work*/ +
                          2 * SOME_MEL_BINS * 4 /*mag*/;
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-// W_2048^idx for idx < 2048 from the half table (W^(j + 1024) = -W^j)
-__device__ __forceinline__ float2 tw2048(const float2* tw, int idx) {
-  const float2 t = tw[idx & 1023];
-  return (idx & 1024) ? make_float2(-t.x, -t.y) : t;
 }
 // position of X[k] after the in-place radix-4 DIF: reverse the five base-4 digits of k
 __device__ __forceinline__ int rev4_10(int k) {
@@ -54,7 +50,7 @@ mel_kernel(const float* __restrict__ wave, const int64_t* __restrict__ clip_star
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float* s_x = reinterpret_cast<float*>(smem_raw);
   float2* s_tw = reinterpret_cast<float2*>(s_x + MEL_NS);
-  float* s_win = reinterpret_cast<float*>(s_tw + 1024);
+  float* s_win = reinterpret_cast<float*>(s_tw + MEL_TW);
   float2* s_work = reinterpret_cast<float2*>(s_win + 2048);
   float* s_mag = reinterpret_cast<float*>(s_work + 2 * 1024);
 
@@ -85,7 +81,7 @@ mel_kernel(const float* __restrict__ wave, const int64_t* __restrict__ clip_star
     }
     *reinterpret_cast<float4*>(s_x + i) = v;
   }
-  for (int i = threadIdx.x; i < 1024; i += 256) s_tw[i] = reinterpret_cast<const float2*>(twiddle)[i];
+  for (int i = threadIdx.x; i < MEL_TW; i += 256) s_tw[i] = reinterpret_cast<const float2*>(twiddle)[i];
   for (int i = threadIdx.x; i < 2048; i += 256) s_win[i] = window[i];
   __syncthreads();
 
@@ -129,10 +125,13 @@ mel_kernel(const float* __restrict__ wave, const int64_t* __restrict__ clip_star
           float2 y2 = make_float2(t0.x - t2.x, t0.y - t2.y);
           float2 y3 = make_float2(t1.x - t3.x, t1.y - t3.y);
           if (s < 4) {  // last stage: all twiddles are 1
-            const int e = (2 * j) << (2 * s);  // W_Lg^j = W_2048^(2 j 4^s)
-            y1 = cmul(y1, tw2048(s_tw, e));
-            y2 = cmul(y2, tw2048(s_tw, 2 * e));
-            y3 = cmul(y3, tw2048(s_tw, 3 * e));
+            // per-stage tables W_Lg^(m j), m = 1..3, j < q, contiguous in j: consecutive threads -> consecutive words
+            // (a single strided W_2048 table made these reads up to 16-way bank conflicted)
+            constexpr int kOff[4] = {0, 768, 960, 1008};
+            const float2* tws = s_tw + kOff[s];
+            y1 = cmul(y1, tws[j]);
+            y2 = cmul(y2, tws[q + j]);
+            y3 = cmul(y3, tws[2 * q + j]);
           }
           z[i0] = y0, z[i1] = y1, z[i2] = y2, z[i3] = y3;
         }
@@ -148,7 +147,7 @@ mel_kernel(const float* __restrict__ wave, const int64_t* __restrict__ clip_star
         const float2 E = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
         const float2 dlt = make_float2(zk.x - zn.x, zk.y + zn.y);  // Z[k] - conj(Z[N-k])
         const float2 O = make_float2(0.5f * dlt.y, -0.5f * dlt.x);  // -i/2 * dlt
-        const float2 wo = cmul(s_tw[k], O);
+        const float2 wo = cmul(s_tw[1020 + k], O);  // W_2048^k
         const float re = E.x + wo.x, im = E.y + wo.y;
         mag[k] = sqrtf(re * re + im * im);
       }

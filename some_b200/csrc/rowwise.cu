@@ -251,8 +251,9 @@ extern "C" int some_dwconv_bn_silu(const some_dwconv_args* a, cudaStream_t strea
   const long long nt = 1ll * p.tiles_per_clip * a->B;
   SOME_REQUIRE(nt < (1ll << 31), "some_dwconv_bn_silu: too many tiles");
   p.num_tiles = static_cast<int>(nt);
-  // persistent grid: ~2 CTAs per SM in total, split evenly over the (channel block, group) pairs
-  const int per_cb = (2 * num_sms() + (D / DW_C) * a->groups - 1) / ((D / DW_C) * a->groups);
+  // persistent grid: 2 CTAs per SM in total (register-limited occupancy), split evenly over the (channel block, group) pairs
+  int per_cb = (2 * num_sms()) / ((D / DW_C) * a->groups);   // floor: every CTA resident in the first (only) wave
+  if (per_cb < 1) per_cb = 1;
   p.ctas_per_cb = static_cast<int>(nt < per_cb ? nt : per_cb);
   dim3 grid(p.ctas_per_cb, D / DW_C, a->groups);
   dwconv_kernel<<<grid, 256, 0, stream>>>(p);

@@ -62,8 +62,19 @@ def mel_tables(config: dict, device) -> Dict[str, torch.Tensor]:
                 f'({_lib.MEL_BINS} bins, {_lib.MEL_MAXW} per filter); fmin/fmax/sr differ from the shipped configs')
         start[m], count[m] = lo, hi - lo + 1
         weights[m, :hi - lo + 1] = bank[m, lo:hi + 1]
-    j = np.arange(1024, dtype=np.float64)
-    tw = np.stack([np.cos(-2.0 * np.pi * j / 2048.0), np.sin(-2.0 * np.pi * j / 2048.0)], axis=1).astype(np.float32)
+    # twiddles of the in-place radix-4 DIF FFT (mel.cu): per stage s (group length L = 1024 / 4^s, q = L / 4) the
+    # factors exp(-2 pi i m j / L), m = 1..3, j < q, contiguous in j; then exp(-2 pi i k / 2048) for the real-FFT unpack
+    parts = []
+    for st in range(4):
+        L = 1024 >> (2 * st)
+        q = L // 4
+        for mm in (1, 2, 3):
+            ang = -2.0 * np.pi * mm * np.arange(q, dtype=np.float64) / L
+            parts.append(np.stack([np.cos(ang), np.sin(ang)], axis=1))
+    ang = -2.0 * np.pi * np.arange(_lib.MEL_BINS, dtype=np.float64) / 2048.0
+    parts.append(np.stack([np.cos(ang), np.sin(ang)], axis=1))
+    tw = np.concatenate(parts, axis=0).astype(np.float32)
+    assert tw.shape == (_lib.MEL_TW, 2)
     n = np.arange(n_fft, dtype=np.float64)
     window = torch.hann_window(n_fft, periodic=True, dtype=torch.float32)    # spec.py:45 torch.hann_window
     return {

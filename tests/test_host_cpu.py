@@ -147,7 +147,9 @@ def test_mel_tables_match_golden_basis(golden_dir):
     assert np.array_equal(dense, ref)
     assert torch.equal(t['window'], torch.hann_window(2048))
     tw = t['twiddle'].double()
-    assert abs(float(tw[512, 0])) < 1e-7 and abs(float(tw[512, 1]) + 1.0) < 1e-7    # W^(N/4) = -i
+    assert tw.shape == (1392, 2)
+    assert abs(float(tw[384, 0])) < 1e-7 and abs(float(tw[384, 1]) + 1.0) < 1e-7    # stage 0, m = 2, j = 128: W_1024^256 = -i
+    assert abs(float(tw[1020 + 256, 0]) - np.cos(-2 * np.pi * 256 / 2048)) < 1e-7   # unpack table W_2048^k
 
 
 # --------------------------------------------------------------------------- sharding + gather
