@@ -168,6 +168,53 @@ typedef struct {
 uint64_t some_decode_scratch_bytes(int M);
 int some_decode_notes(const some_decode_args* args, cudaStream_t stream);
 
+/* ---- some_forward: the whole trunk Gmidi_conform.forward (Gconform.py:119-140) + head activation
+ * (Gmidi_conform.py:30-40) as one call that enqueues the launch sequence above on `stream`.
+ * All pointers are device pointers owned by the caller (packed by some_b200/weights.py); the structs themselves are
+ * host memory and are only read during the call. */
+typedef struct {
+  const float* ln_g[5];        /* norm1..norm5 weight / bias, f32 [512] */
+  const float* ln_b[5];
+  const uint16_t* ffn_w1[2];   /* ffn1 / ffn2: ln1 bf16 [2048,512], ln2 bf16 [512,2048] */
+  const float* ffn_b1[2];
+  const uint16_t* ffn_w2[2];
+  const float* ffn_b2[2];
+  const uint16_t* w_qkv;       /* bf16 [1536,512] = to_q | to_kv */
+  const uint16_t* w_out;       /* bf16 [512,512] */
+  const float* b_out;
+  const uint16_t* w_pw1;       /* bf16 [1024,512], GLU-packed rows */
+  const float* b_pw1;
+  const float* w_dw;           /* f32 [31][512], BatchNorm folded */
+  const float* b_dw;
+  const uint16_t* w_pw2;       /* bf16 [512,512] */
+  const float* b_pw2;
+} some_block_weights;
+typedef struct {
+  int lay, outdim;
+  const uint16_t* w_in[2];     /* inln / inln1 bf16 [512,80] */
+  const float* b_in[2];
+  const some_block_weights* blocks; /* host array [(lay + 1) * 2]: entry 2 i + s = block i of stream s (0 = att1, 1 = att2) */
+  const uint16_t* const* glu_w;     /* host array [lay * 2]: entry 2 i + 0 = glu1 (fed by midi), 2 i + 1 = glu2, GLU-packed */
+  const float* const* glu_b;
+  const uint16_t* w_head;      /* outln bf16 [outdim,512] */
+  const float* b_head;         /* f32, padded to a multiple of 32 */
+  const float* w_cut;          /* cutheard f32 [512] */
+  float b_cut;
+} some_model;
+typedef struct {
+  float* x[2];                 /* f32 [M,512] residual streams */
+  uint16_t* a[2];              /* bf16 [M,512] */
+  uint16_t* h[2];              /* bf16 [M,2048] */
+  uint16_t* qkv[2];            /* bf16 [M,1536] */
+  uint16_t* g[2];              /* bf16 [M,512] */
+  const uint16_t* units;       /* bf16 [M,80] log-mel (input) */
+  float* probs;                /* f32 [M,outdim] (output) */
+  float* bounds;               /* f32 [M] (output) */
+} some_workspace;
+/* head: SOME_EPI_SIGMOID_F32 (sig=True), SOME_EPI_SOFTMAX_F32 (softmax=True) or SOME_EPI_BIAS_F32 (raw logits) */
+int some_forward(const some_model* model, const some_workspace* ws, int M, int B, const int32_t* cu_frames,
+                 int max_frames, int head, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

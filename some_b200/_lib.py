@@ -47,6 +47,23 @@ class DecodeArgs(C.Structure):
                 ('dbg_rest', _vp), ('scratch', _vp)]
 
 
+class BlockWeightsC(C.Structure):
+    _fields_ = [('ln_g', _vp * 5), ('ln_b', _vp * 5), ('ffn_w1', _vp * 2), ('ffn_b1', _vp * 2), ('ffn_w2', _vp * 2),
+                ('ffn_b2', _vp * 2), ('w_qkv', _vp), ('w_out', _vp), ('b_out', _vp), ('w_pw1', _vp), ('b_pw1', _vp),
+                ('w_dw', _vp), ('b_dw', _vp), ('w_pw2', _vp), ('b_pw2', _vp)]
+
+
+class ModelC(C.Structure):
+    _fields_ = [('lay', C.c_int), ('outdim', C.c_int), ('w_in', _vp * 2), ('b_in', _vp * 2),
+                ('blocks', C.POINTER(BlockWeightsC)), ('glu_w', C.POINTER(_vp)), ('glu_b', C.POINTER(_vp)),
+                ('w_head', _vp), ('b_head', _vp), ('w_cut', _vp), ('b_cut', C.c_float)]
+
+
+class WorkspaceC(C.Structure):
+    _fields_ = [('x', _vp * 2), ('a', _vp * 2), ('h', _vp * 2), ('qkv', _vp * 2), ('g', _vp * 2), ('units', _vp),
+                ('probs', _vp), ('bounds', _vp)]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     'some_version': (C.c_int, []),
@@ -61,6 +78,7 @@ EXPORTS = {
     'some_bound_head': (C.c_int, [_vp, _vp, _vp, _vp, C.c_float, C.c_int, _vp, _vp]),
     'some_decode_scratch_bytes': (C.c_uint64, [C.c_int]),
     'some_decode_notes': (C.c_int, [C.POINTER(DecodeArgs), _vp]),
+    'some_forward': (C.c_int, [C.POINTER(ModelC), C.POINTER(WorkspaceC), C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp]),
 }
 
 _lib = None

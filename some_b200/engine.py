@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from .config import DIM, FFN_DIM, check_supported
-from .weights import ModelWeights, mel_tables
+from .weights import ModelWeights, build_c_model, mel_tables
 
 HOP = 512
 
@@ -44,6 +44,11 @@ class _Workspace:
         self.note_dur = torch.empty((m,), dtype=torch.int32, device=device)
         self.note_rest = torch.empty((m,), dtype=torch.uint8, device=device)
         self.scratch = torch.empty((int(_lib.load().some_decode_scratch_bytes(m)),), dtype=torch.uint8, device=device)
+        c = self.c = _lib.WorkspaceC()                    # some_workspace for the native sequencer
+        for s in range(2):
+            c.x[s], c.a[s], c.h[s] = self.x[s].data_ptr(), self.a[s].data_ptr(), self.h[s].data_ptr()
+            c.qkv[s], c.g[s] = self.qkv[s].data_ptr(), self.g[s].data_ptr()
+        c.units, c.probs, c.bounds = self.units.data_ptr(), self.probs.data_ptr(), self.bounds.data_ptr()
 
 
 class Engine:
@@ -56,12 +61,15 @@ class Engine:
             raise _lib.SomeB200Error('some_b200 runs on CUDA devices only (sm_100a); there is no CPU path')
         self.quantized = False
         self.w = ModelWeights(state_dict, config, self.device)
+        self._cmodel, self._cmodel_keep = build_c_model(self.w)
         self.mel = mel_tables(config, self.device)
         self.outdim = config['midi_num_bins']
         self.timestep = config['hop_size'] / config['audio_sample_rate']
         self._ws: Optional[_Workspace] = None
         self.launches = 0
         self._sum_t2 = 0.0
+        # launches of one trunk pass: inln + (lay + 1) blocks x 15 + lay GLU mixes + (final LN + bound head - LN5) + head
+        self.trunk_launches = 1 + 15 * (self.w.lay + 1) + self.w.lay + 1 + 1
         # optional per-kernel timing: name -> [(start_event, end_event, work)] where work = FLOPs (GEMM,
         # attention) or algorithmic bytes (HBM-bound kernels); enabled by bench.py via start_profile()
         self.prof: Optional[dict] = None
@@ -207,6 +215,14 @@ class Engine:
         (Gmidi_conform.py:30-40).  Reads ws.units; writes ws.probs [m, outdim] and ws.bounds [m].
         head: 'sigmoid' | 'softmax' | 'logits'."""
         w, x, a = self.w, ws.x, ws.a
+        epi = {'sigmoid': _lib.EPI_SIGMOID_F32, 'softmax': _lib.EPI_SOFTMAX_F32, 'logits': _lib.EPI_BIAS_F32}[head]
+        if self.prof is None and taps is None:
+            # product path: one native call enqueues the whole launch sequence (csrc/forward.cu)
+            _lib.check(self.lib.some_forward(C.byref(self._cmodel), C.byref(ws.c), m, b, cu_frames.data_ptr(), max_frames,
+                                             epi, self._stream), 'some_forward')
+            self.launches += self.trunk_launches
+            return
+        # per-kernel path (CUDA events around every launch / intermediate taps): same sequence, driven from Python
         # QK^T + PV MACs of one attention launch (both streams): 2 * 8 heads * 64 * sum T^2 (profiling only; the clip
         # lengths come from the host copy of cu_frames so that no device sync sneaks into the timed region)
         self._att_flops = float(2 * 2 * 512 * self._sum_t2) if self.prof is not None else 0.0
@@ -221,7 +237,6 @@ class Engine:
                 taps[f'model.cf_lay.{i}:midi'] = x[0, :m].clone()
                 taps[f'model.cf_lay.{i}:bound'] = x[1, :m].clone()
         self._block(ws, w.blocks[w.lay], m, b, cu_frames, max_frames, last=True)
-        epi = {'sigmoid': _lib.EPI_SIGMOID_F32, 'softmax': _lib.EPI_SOFTMAX_F32, 'logits': _lib.EPI_BIAS_F32}[head]
         self._gemm(a[0], None, w.w_head, None, w.b_head, None, ws.probs, None, None, None,
                    m, self.outdim, DIM, DIM, self.outdim, epi, groups=1)          # outln (+ sigmoid / softmax)
 
@@ -288,21 +303,25 @@ class Engine:
             self._stage = st
         return st
 
-    # number of pipeline chunks a large batch is split into so that host staging + H2D of chunk c+1 overlap the
-    # kernels of chunk c (each chunk keeps >= MIN_CHUNK_FRAMES rows so the GEMM / attention grids stay full)
-    MAX_CHUNKS = 4
-    MIN_CHUNK_FRAMES = 32768
+    # Pipeline chunks of a large batch: staging + H2D of chunk c+1 overlap the kernels of chunk c.  Small chunks cost
+    # kernel efficiency (measured on 64 x 30 s: 1 / 2 / 4 / 8 equal chunks -> 38.0 / 38.9 / 40.7 / 44.9 ms of kernels), so
+    # the split is geometric: a small first chunk gets the GPU going, the later ones stay big.
+    CHUNK_FRACTIONS = (0.125, 0.375, 0.5)
+    MIN_CHUNK_FRAMES = 16384
 
     def _chunks(self, cu: np.ndarray) -> List[tuple]:
         b, m = len(cu) - 1, int(cu[-1])
-        n = int(max(1, min(self.MAX_CHUNKS, b, m // self.MIN_CHUNK_FRAMES)))
-        bounds = [0]
-        for c in range(1, n):
-            target = m * c / n
-            i = int(np.searchsorted(cu, target, side='left'))
-            bounds.append(min(max(i, bounds[-1] + 1), b - (n - c)))
+        if b < 2 or m < 2 * self.MIN_CHUNK_FRAMES:
+            return [(0, b)]
+        bounds, acc = [0], 0.0
+        for f in self.CHUNK_FRACTIONS[:-1]:
+            acc += f
+            i = int(np.searchsorted(cu, acc * m, side='left'))
+            i = min(max(i, bounds[-1] + 1), b - 1)
+            if cu[i] - cu[bounds[-1]] >= self.MIN_CHUNK_FRAMES // 2 and i > bounds[-1]:
+                bounds.append(i)
         bounds.append(b)
-        return [(bounds[i], bounds[i + 1]) for i in range(n)]
+        return [(bounds[i], bounds[i + 1]) for i in range(len(bounds) - 1) if bounds[i + 1] > bounds[i]]
 
     def _pool(self):
         if getattr(self, '_tp', None) is None:
@@ -314,8 +333,8 @@ class Engine:
     def infer(self, waveforms: Sequence[np.ndarray], quantized: bool = False,
               return_intermediates: bool = False) -> List[Dict[str, np.ndarray]]:
         """waveform-in -> notes-out for a list of clips: the batched equivalent of BaseInference.infer
-        (base_infer.py:46-53).  Host buffers in, host buffers out.  The batch is cut into up to 4 chunks of whole
-        clips; for each chunk the clips are staged into pinned memory by a small thread pool (memcpy releases the
+        (base_infer.py:46-53).  Host buffers in, host buffers out.  The batch is cut into up to 3 chunks of whole
+        clips (small first chunk); for each chunk the clips are staged into pinned memory by a small thread pool (memcpy releases the
         GIL), copied H2D on a copy stream, and the kernels of the chunk are enqueued behind an event — so staging and
         H2D of chunk c+1 overlap the kernels of chunk c.  The notes of each chunk come back in ONE packed D2H copy
         [counts | dur | midi | rest]; there is a single host synchronisation at the end."""

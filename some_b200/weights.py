@@ -153,3 +153,40 @@ class ModelWeights:
         self.w_cut = f32(sd['model.cutheard.weight'][0])                 # [512]
         self.b_cut = float(sd['model.cutheard.bias'][0])
         assert self.w_in[0].shape == (DIM, config['units_dim'])
+
+
+def build_c_model(w: ModelWeights):
+    """ctypes mirror (include/some_b200.h: some_model) of the packed weights for the native launch sequencer
+    some_forward.  Returns (ModelC, keepalive): the struct only holds raw pointers, `keepalive` owns the arrays."""
+    import ctypes as C
+    nblk = (w.lay + 1) * 2
+    blocks = (_lib.BlockWeightsC * nblk)()
+    for i, pair in enumerate(w.blocks):
+        for s, bw in enumerate(pair):
+            b = blocks[2 * i + s]
+            for k in range(5):
+                b.ln_g[k], b.ln_b[k] = bw.ln_g[k].data_ptr(), bw.ln_b[k].data_ptr()
+            for k in range(2):
+                f = bw.ffn[k]
+                b.ffn_w1[k], b.ffn_b1[k] = f['w1'].data_ptr(), f['b1'].data_ptr()
+                b.ffn_w2[k], b.ffn_b2[k] = f['w2'].data_ptr(), f['b2'].data_ptr()
+            b.w_qkv, b.w_out, b.b_out = bw.w_qkv.data_ptr(), bw.w_out.data_ptr(), bw.b_out.data_ptr()
+            b.w_pw1, b.b_pw1 = bw.w_pw1.data_ptr(), bw.b_pw1.data_ptr()
+            b.w_dw, b.b_dw = bw.w_dw.data_ptr(), bw.b_dw.data_ptr()
+            b.w_pw2, b.b_pw2 = bw.w_pw2.data_ptr(), bw.b_pw2.data_ptr()
+    n_glu = max(w.lay * 2, 1)
+    glu_w = (C.c_void_p * n_glu)()
+    glu_b = (C.c_void_p * n_glu)()
+    for i in range(w.lay):
+        for s in range(2):
+            glu_w[2 * i + s] = w.glu_w[i][s].data_ptr()
+            glu_b[2 * i + s] = w.glu_b[i][s].data_ptr()
+    m = _lib.ModelC()
+    m.lay, m.outdim = w.lay, w.outdim
+    for s in range(2):
+        m.w_in[s], m.b_in[s] = w.w_in[s].data_ptr(), w.b_in[s].data_ptr()
+    m.blocks = C.cast(blocks, C.POINTER(_lib.BlockWeightsC))
+    m.glu_w = C.cast(glu_w, C.POINTER(C.c_void_p))
+    m.glu_b = C.cast(glu_b, C.POINTER(C.c_void_p))
+    m.w_head, m.b_head, m.w_cut, m.b_cut = w.w_head.data_ptr(), w.b_head.data_ptr(), w.w_cut.data_ptr(), w.b_cut
+    return m, (blocks, glu_w, glu_b)

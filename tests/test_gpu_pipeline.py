@@ -91,13 +91,34 @@ def test_batched_equals_per_clip(tmp_path):
             np.testing.assert_array_equal(rb[k], single[k])
 
 
+def test_native_sequencer_equals_per_kernel_path(tmp_path):
+    """some_forward (C++ launch sequencer, the product path) and the per-kernel Python path must enqueue the same work."""
+    ins, _ = _plugin('two_head', tmp_path)
+    eng = ins.model
+    frames = [300, 41, 129]
+    m, b = sum(frames), len(frames)
+    cu = torch.tensor(np.cumsum([0] + frames), dtype=torch.int32, device=eng.device)
+    ws = eng.workspace(m)
+    torch.manual_seed(0)
+    ws.units[:m].copy_(torch.randn(m, 80, device=eng.device) * 3 - 4)
+    out = {}
+    for name, taps in (('native', None), ('python', {})):
+        ws.probs.fill_(float('nan'))
+        ws.bounds.fill_(float('nan'))
+        eng.run_trunk(ws, m, b, cu, max(frames), 'sigmoid', taps=taps)
+        torch.cuda.synchronize()
+        out[name] = (ws.probs[:m].clone(), ws.bounds[:m].clone())
+    assert torch.equal(out['native'][0], out['python'][0]) and torch.equal(out['native'][1], out['python'][1])
+    assert not torch.isnan(out['native'][0]).any()
+
+
 def test_chunked_pipeline_equals_single_chunk(tmp_path):
     """infer() cuts big batches into pipeline chunks (staging / H2D overlap); results must not depend on it."""
     ins, _ = _plugin('two_head', tmp_path)
     waves = [synth.synth_waveform(500 + i, seconds=s) for i, s in enumerate([1.3, 0.7, 2.2, 0.4, 1.9, 1.1, 0.9])]
     whole = ins.infer(waves)
-    ins.model.MIN_CHUNK_FRAMES = 64           # force 4 chunks
-    assert len(ins.model._chunks(np.cumsum([0] + [synth.frames_of(len(w)) for w in waves]).astype(np.int32))) == 4
+    ins.model.MIN_CHUNK_FRAMES = 64           # force several chunks
+    assert len(ins.model._chunks(np.cumsum([0] + [synth.frames_of(len(w)) for w in waves]).astype(np.int32))) >= 2
     chunked = ins.infer(waves)
     for a, b in zip(whole, chunked):
         for k in ('note_midi', 'note_dur', 'note_rest'):
