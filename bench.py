@@ -75,7 +75,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix='.csv')
             os.close(fd)
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-lms', '100', '-i', str(self.gpu_index)],
+                                          '-lms', '50', '-i', str(self.gpu_index)],
                                          stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -122,7 +122,7 @@ def time_cpu_reference(clips, threads=None):
     config = synth.named_config(CONFIG_NAME)
     sd = synth.fabricate_state_dict(config, seed=1234)
     t0 = time.perf_counter()
-    odecode.infer(sd, config, clips)
+    odecode.infer(sd, config, clips, quantized=CONFIG_NAME.startswith('quant'))
     dt = time.perf_counter() - t0
     return sum(len(c) for c in clips) / synth.SR / dt, dt
 
@@ -180,8 +180,10 @@ def run_ours(args, rank, world, local_rank):
     import contextlib
     with tempfile.TemporaryDirectory() as d, contextlib.redirect_stdout(sys.stderr):   # stdout = the ONE JSON line
         ckpt = synth.write_checkpoint(d, config, seed=1234)
-        ins = plugin.MIDIExtractionInference(config=config, model_path=ckpt, device=f'cuda:{local_rank}')
+        cls = plugin.QuantizedMIDIExtractionInference if CONFIG_NAME.startswith('quant') else plugin.MIDIExtractionInference
+        ins = cls(config=config, model_path=ckpt, device=f'cuda:{local_rank}')
     eng = ins.model
+    quant = CONFIG_NAME.startswith('quant')
     clips = make_clips(rank * CLIPS_PER_GPU, CLIPS_PER_GPU, CLIP_SECONDS)
     audio_seconds_rank = sum(len(c) for c in clips) / synth.SR
     lengths_all = [len(c) for c in clips] * world           # every rank's clips have the same lengths
@@ -202,8 +204,8 @@ def run_ours(args, rank, world, local_rank):
 
     def device_step():
         eng.run_mel(wave, tables_d[:b], tables_d[b:], cu_d, b, max_frames, None, ws.units)
-        eng.run_trunk(ws, m, b, cu_d, max_frames, 'sigmoid')
-        eng.run_decode(ws, m, b, cu_d, note_count, False)
+        eng.run_trunk(ws, m, b, cu_d, max_frames, 'softmax' if quant else 'sigmoid')
+        eng.run_decode(ws, m, b, cu_d, note_count, quant)
 
     for _ in range(max(args.warmup, 3)):
         device_step()
@@ -294,7 +296,7 @@ def run_ours(args, rank, world, local_rank):
         'warmup': max(args.warmup, 3), 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'clips_per_gpu': CLIPS_PER_GPU, 'clip_seconds': CLIP_SECONDS,
-                   'frames_per_gpu': m, 'parallelism': f'dp{world}', 'l2': 'inputs (339 MB audio, >1 GB activations) exceed the 126 MB L2',
+                   'frames_per_gpu': m, 'parallelism': f'dp{world}', 'l2': f'inputs ({host.numel() * 4 / 1e6:.0f} MB audio, {m * 512 * 4 * 2 / 1e9:.1f} GB residual streams) exceed the 126 MB L2',
                    'weights': 'seeded random (no pretrained checkpoint offline)'},
         'e2e': {'value': e2e_value, 'unit': 'audio-s/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': e2e_ms / args.steps},
@@ -319,7 +321,16 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--ref-clips', type=int, default=8, help='bounded CPU sample: clips per CPU step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    # extra measurements for the BASELINE.md table (the default = the contract workload, BASELINE.json configs[1])
+    ap.add_argument('--config', default='two_head', choices=['two_head', 'quant_two_head', 'midi_conformer'])
+    ap.add_argument('--clips', type=int, default=64, help='clips per GPU')
+    ap.add_argument('--seconds', type=float, default=30.0, help='clip length')
     args = ap.parse_args()
+    global CONFIG_NAME, CLIPS_PER_GPU, CLIP_SECONDS, WORKLOAD
+    CONFIG_NAME, CLIPS_PER_GPU, CLIP_SECONDS = args.config, args.clips, args.seconds
+    yaml_name = {'two_head': 'two_head_model', 'quant_two_head': 'quant_two_head_model', 'midi_conformer': 'midi_conformer'}[args.config]
+    WORKLOAD = (f'configs/{yaml_name}.yaml, batch={args.clips}x{args.seconds:g} s synthetic 44.1 kHz mono clips per GPU, '
+                f'bf16 operands')
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
