@@ -5,15 +5,15 @@
 // output bf16 [M, 512] = 'b h t c -> b t (h c)'.  No head-major copies are made: Q/K/V tiles are TMA boxes cut
 // straight out of qkv.
 //
-// CTA = 128 query rows of one (clip, head), 64-key tiles; 2 CTAs per SM (96 KB smem, 256 TMEM columns each).
+// CTA = 128 query rows of one (clip, head), 64-key tiles; 2 CTAs per SM (80 KB smem, 256 TMEM columns each).
 // Roles (256 threads):
 //   warp 0   TMA producer: Q once, then (K_j, V_j) 64-key tiles into a 4-stage ring (128-B swizzle)
 //   warp 1   MMA issuer (one thread):  S_j = Q K_j^T  (tcgen05.mma M128 N64 K16 x4, both operands K-major) into one of
 //            TWO S buffers, so QK_{j+2} is issued as soon as the softmax has consumed S_j and the softmax never waits
-//            for the tensor core in steady state;  O += P_j V_j  (M128 N64 K16 x4, A = P from smem, B = V MN-major)
+//            for the tensor core in steady state;  O += P_j V_j  (M128 N64 K16 x4, A = P from TENSOR MEMORY, B = V MN-major)
 //   warp 2   TMEM allocator: S0 | S1 | O, 64 fp32 columns each
 //   warps 4-7 softmax, thread = query row: ONE tcgen05.ld of the 64 scores, online softmax in base 2 (ex2.approx), P ->
-//            bf16 -> smem (double-buffered) in the UMMA K-major swizzled layout.  O stays in TMEM and is rescaled
+//            bf16 pairs -> tcgen05.st over the first half of the S buffer just read.  O stays in TMEM and is rescaled
 //            (tcgen05.ld / st) only when some row maximum of the warp grew by more than 2^8 ("lazy rescale": otherwise
 //            the stale maximum is kept, P <= 256, exact after the final division by the row sum).
 // Rows of K/V beyond the clip end are masked (p = 0); rows beyond M are zero-filled by TMA.
@@ -29,8 +29,7 @@ constexpr int TC_BN = 64;                  // keys per tile
 constexpr int TC_QTILE = 128 * 64 * 2;     // 16 KB
 constexpr int TC_KTILE = TC_BN * 64 * 2;   // 8 KB (K or V tile)
 constexpr int TC_STAGES = 4;  // K/V tile j+3 is requested when PV_{j-1} retires: two tile periods to cover the TMA latency
-constexpr int TC_PTILE = 128 * TC_BN * 2;  // 16 KB
-constexpr int TC_SMEM = TC_QTILE + TC_STAGES * 2 * TC_KTILE + 2 * TC_PTILE + 128 /*barriers*/;
+constexpr int TC_SMEM = TC_QTILE + TC_STAGES * 2 * TC_KTILE + 128 /*barriers*/;
 constexpr uint32_t TC_TMEM_COLS = 256;
 constexpr uint32_t TC_O_COL = 128;
 
@@ -53,8 +52,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sKV = smem + TC_QTILE;                                  // stage s: K at +s * 2 * KTILE, V right after it
-  uint8_t* sP = sKV + TC_STAGES * 2 * TC_KTILE;                    // two P buffers, one 64-key K-major atom each
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * TC_PTILE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + TC_STAGES * 2 * TC_KTILE);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;    // [4]
   uint64_t* kv_empty = bars + 5;   // [4]
@@ -141,11 +139,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
         const int s = j % TC_STAGES;
         mbar_wait(&p_full[j & 1], (j >> 1) & 1);  // P_j in smem (and O rescaled if it had to be)
         tc_fence_after_sync();
-        const uint64_t pdesc = umma_desc_kmajor_sw128(smem_u32(sP + (j & 1) * TC_PTILE));
         const uint64_t vdesc = umma_desc_mnmajor_sw128(smem_u32(sKV + s * 2 * TC_KTILE + TC_KTILE), 1024);
+        const uint32_t p_tmem = tmem_base + (j & 1) * TC_BN;  // P_j (bf16, two keys per column) overwrote S_j's first 32 columns
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // 16 keys per MMA: A +32 B inside the swizzle atom (+2), B +16 key rows = 2 KB (+128)
-          umma_bf16_ss(tmem_base + TC_O_COL, pdesc + 2 * k, vdesc + 128 * k, idesc_pv, (j | k) != 0);
+        for (int k = 0; k < 4; ++k)  // 16 keys per MMA: A +8 TMEM columns, B +16 key rows = 2 KB (+128)
+          umma_bf16_ts(tmem_base + TC_O_COL, p_tmem + 8 * k, vdesc + 128 * k, idesc_pv, (j | k) != 0);
         umma_commit(&pv_done[j & 1]);
         umma_commit(&kv_empty[s]);
         // S[j & 1] has been consumed (p_full_j): refill it two tiles ahead so the softmax never waits for the MMAs
@@ -160,7 +158,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
     const uint32_t t_o = t_lane + TC_O_COL;
     const float c = 0.125f * 1.4426950408889634f;  // dim_head^-0.5 * log2(e)
     float m_used = -INFINITY, l = 0.f;
-    const int sw = r & 7;
     for (int j = 0; j < n_tiles; ++j) {
       const int valid = min(TC_BN, T - j * TC_BN);  // keys of this tile inside the clip
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
@@ -233,13 +230,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
         tmem_st_32x32(t_o + 32, hi);
         tmem_st_wait();
       }
-      // ---- P -> smem (UMMA K-major, 128-B swizzle: 16-byte chunk index XOR (row & 7)).  Buffer j & 1 was last read by
-      //      PV_{j-2}, which completed before s_full_j was signalled (QK_j was issued after it).
-      uint8_t* prow = sP + (j & 1) * TC_PTILE + r * 128;
-#pragma unroll
-      for (int ch = 0; ch < 8; ++ch)
-        *reinterpret_cast<uint4*>(prow + ((ch ^ sw) << 4)) = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
-      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      // ---- P -> TMEM: bf16 pairs into the first 32 columns of this row's S_j (all 64 scores are in registers by now); the
+      //      PV MMA takes its A operand straight from tensor memory, so P never touches shared memory: no 16 KB store, no
+      //      generic->async proxy fence, and the tensor core re-reads 4 KB less smem per MMA.  QK_{j+2} overwrites these
+      //      columns only after PV_j (the MMA pipe executes in issue order).
+      tmem_st_32x32(t_lane + (j & 1) * TC_BN, pk);
+      tmem_st_wait();
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[j & 1]);
