@@ -29,14 +29,15 @@ struct LnParams {
 };
 
 // one warp per row: lane holds columns {128 i + 4 lane .. +3}, i < 4 (coalesced float4)
-__device__ __forceinline__ void ln_row(const float* __restrict__ xr, const float* __restrict__ gamma,
-                                       const float* __restrict__ beta, int lane, float (&y)[16]) {
-  float v[16];
+__device__ __forceinline__ void ln_load(const float* __restrict__ xr, int lane, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float4 t = *reinterpret_cast<const float4*>(xr + 128 * i + 4 * lane);
     v[4 * i] = t.x, v[4 * i + 1] = t.y, v[4 * i + 2] = t.z, v[4 * i + 3] = t.w;
   }
+}
+__device__ __forceinline__ void ln_normalise(const float (&v)[16], const float* __restrict__ gamma,
+                                             const float* __restrict__ beta, int lane, float (&y)[16]) {
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < 16; ++i) s += v[i];
@@ -58,14 +59,13 @@ __device__ __forceinline__ void ln_row(const float* __restrict__ xr, const float
     y[4 * i + 3] = fmaf((v[4 * i + 3] - mean) * rstd, g.w, b.w);
   }
 }
-
-__global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
-  const int grp = blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= p.M) return;
-  float y[16];
-  ln_row(p.x[grp] + (size_t)row * D, p.gamma[grp], p.beta[grp], lane, y);
+__device__ __forceinline__ void ln_row(const float* __restrict__ xr, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, int lane, float (&y)[16]) {
+  float v[16];
+  ln_load(xr, lane, v);
+  ln_normalise(v, gamma, beta, lane, y);
+}
+__device__ __forceinline__ void ln_store(const LnParams& p, int grp, int row, int lane, const float (&y)[16]) {
   if (p.out_f32[grp] != nullptr) {
     float* o = p.out_f32[grp] + (size_t)row * D;
 #pragma unroll
@@ -78,6 +78,28 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
     for (int i = 0; i < 4; ++i)
       *reinterpret_cast<uint2*>(o + 128 * i + 4 * lane) =
           make_uint2(pack_bf16x2(y[4 * i], y[4 * i + 1]), pack_bf16x2(y[4 * i + 2], y[4 * i + 3]));
+  }
+}
+
+// Each warp streams LN_RPW rows per pass with all their loads issued up front (128 B per lane in flight): the kernel is a
+// pure HBM stream and memory-level parallelism is what sets its bandwidth.
+constexpr int LN_RPW = 2;
+__global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
+  const int grp = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int row0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * LN_RPW;
+  if (row0 >= p.M) return;
+  float v[LN_RPW][16];
+#pragma unroll
+  for (int r = 0; r < LN_RPW; ++r)
+    if (row0 + r < p.M) ln_load(p.x[grp] + (size_t)(row0 + r) * D, lane, v[r]);
+#pragma unroll
+  for (int r = 0; r < LN_RPW; ++r) {
+    if (row0 + r < p.M) {
+      float y[16];
+      ln_normalise(v[r], p.gamma[grp], p.beta[grp], lane, y);
+      ln_store(p, grp, row0 + r, lane, y);
+    }
   }
 }
 
@@ -221,7 +243,7 @@ extern "C" int some_layernorm(const some_ln_args* a, cudaStream_t stream) {
     p.out_f32[g] = a->out_f32[s];
   }
   p.M = a->M;
-  dim3 grid((a->M + 7) / 8, a->groups);
+  dim3 grid((a->M + 8 * LN_RPW - 1) / (8 * LN_RPW), a->groups);
   layernorm_kernel<<<grid, 256, 0, stream>>>(p);
   return check_launch("some_layernorm");
 }
