@@ -233,11 +233,15 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---------------- end-to-end arm ("e2e"): host numpy in, host numpy out, through the plugin
+    all_clips = None
+    if world > 1:
+        # every rank needs the LENGTHS of all clips (they are identical here); only its own shard's samples are touched
+        all_clips = [clips[i % CLIPS_PER_GPU] for i in range(world * CLIPS_PER_GPU)]
+
     def e2e_step():
-        local = ins.infer(clips)
         if world > 1:
-            return sdist.gather_results(local, lengths_all, shards, ins.timestep, device=dev)
-        return local
+            return sdist.infer_sharded(ins, all_clips)      # shard -> infer -> ONE NCCL all-gather of the packed notes
+        return ins.infer(clips)
 
     for _ in range(max(1, min(args.warmup, 2))):
         e2e_step()

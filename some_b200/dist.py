@@ -111,10 +111,36 @@ def gather_results(local: List[Dict[str, np.ndarray]], lengths: Sequence[int], s
 
 def infer_sharded(plugin, waveforms: Sequence[np.ndarray], group=None) -> List[Dict[str, np.ndarray]]:
     """Data-parallel ``infer``: every rank holds the same ``waveforms`` list (or at least its own shard's
-    entries), processes its shard and all ranks return the full ordered result list."""
+    entries), processes its shard and all ranks return the full ordered result list.
+
+    With the CUDA engine and NCCL the decode kernel's packed note slab never takes a detour through Python: each rank
+    enqueues its shard, the device slabs are all-gathered (one ``all_gather_into_tensor`` over NVLink), and the gathered
+    buffer is copied to the host once and unpacked with the layouts every rank can derive from the clip lengths."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     lengths = [int(w.shape[0]) for w in waveforms]
     shards = shard_clips(lengths, world)
+    eng = getattr(plugin, 'model', None)
+    if dist.get_backend(group) == 'nccl' and hasattr(eng, 'enqueue'):
+        import threading
+        layouts = [eng.slab_layout([lengths[i] for i in s]) if s else (np.zeros(1, np.int32), [], 0) for s in shards]
+        nbytes = max(16, max(l[2] for l in layouts))
+        with getattr(plugin, '_lock', threading.Lock()), torch.cuda.device(eng.device):
+            mine = [waveforms[i] for i in shards[rank]]
+            gathered = torch.empty(world * nbytes, dtype=torch.uint8, device=eng.device)
+            slot = gathered[rank * nbytes:(rank + 1) * nbytes]
+            if mine:
+                slab, _, _, _ = eng.enqueue(mine, quantized=getattr(plugin, 'quantized', False))
+                slot[:slab.numel()].copy_(slab, non_blocking=True)
+            dist.all_gather_into_tensor(gathered, slot.clone(), group=group)
+            host = gathered.cpu().numpy()
+        merged: List[Dict[str, np.ndarray]] = [None] * len(lengths)  # type: ignore
+        for r in range(world):
+            cu_r, layout_r, _ = layouts[r]
+            if not layout_r:
+                continue
+            for idx, res in zip(shards[r], eng.unpack_slab(host[r * nbytes:(r + 1) * nbytes], cu_r, layout_r)):
+                merged[idx] = res
+        return merged
     local = plugin.infer([waveforms[i] for i in shards[rank]])
-    dev = getattr(getattr(plugin, 'model', None), 'device', None) if dist.get_backend(group) == 'nccl' else None
+    dev = getattr(eng, 'device', None) if dist.get_backend(group) == 'nccl' else None
     return gather_results(local, lengths, shards, plugin.timestep, device=dev, group=group)

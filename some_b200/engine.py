@@ -327,101 +327,128 @@ class Engine:
         if getattr(self, '_tp', None) is None:
             import concurrent.futures
             import os
-            self._tp = concurrent.futures.ThreadPoolExecutor(max_workers=min(8, max(2, (os.cpu_count() or 4) // 2)))
+            # staging threads: memcpy-bound; leave cores to the other ranks of a one-process-per-GPU job
+            local_world = int(os.environ.get('LOCAL_WORLD_SIZE', '1') or 1)
+            cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 4)
+            self._tp = concurrent.futures.ThreadPoolExecutor(max_workers=min(8, max(2, cores // (2 * local_world))))
         return self._tp
+
+    def slab_layout(self, lens: Sequence[int]):
+        """Deterministic layout of the packed note slab of a batch with these clip lengths: per pipeline chunk
+        (c0, c1, byte offset, clips, frames) and the total size.  Chunk slab = [counts i32 [bc] | dur i32 [mc] | midi f32 [mc]
+        | rest u8 [mc]].  Every rank of a data-parallel job can compute every other rank's layout from the lengths alone."""
+        _, _, cu, _ = self.tables(lens)
+        layout, off = [], 0
+        for c0, c1 in self._chunks(cu):
+            bc, mc = c1 - c0, int(cu[c1] - cu[c0])
+            layout.append((c0, c1, off, bc, mc))
+            off += (4 * bc + 9 * mc + 15) & ~15
+        return cu, layout, off
+
+    def enqueue(self, waveforms: Sequence[np.ndarray], quantized: bool = False, return_intermediates: bool = False):
+        """Stages, copies and enqueues the whole batch WITHOUT synchronising.  Returns (device slab uint8 [nbytes], cu, layout,
+        extra): the decoded notes land in the device slab (see slab_layout); the caller copies it to the host (infer) or
+        hands it to the all-gather (dist.infer_sharded)."""
+        b = len(waveforms)
+        starts, lens, cu, total = self.tables([int(w.shape[0]) for w in waveforms])
+        m = int(cu[-1])
+        dev = self.device
+        if return_intermediates:
+            layout, nbytes_total = [(0, b, 0, b, m)], (4 * b + 9 * m + 15) & ~15
+        else:
+            _, layout, nbytes_total = self.slab_layout(lens)
+        st = self._staging(total, b, m)
+        stream = torch.cuda.current_stream(dev)
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        copy_stream = self._copy_stream
+        copy_stream.wait_stream(stream)       # previous users of the staging / device buffers are done
+        wave_h, wave_d, tab_h, tab_d, out_d = (st[k] for k in ('wave_h', 'wave_d', 'tab_h', 'tab_d', 'out_d'))
+        hv = wave_h.numpy()
+        pool = self._pool()
+
+        def stage(i):
+            n = int(lens[i])
+            if n:
+                hv[starts[i]:starts[i] + n] = waveforms[i]          # dtype cast (if any) + memcpy, GIL released
+
+        ws = self.workspace(max(mc for *_, mc in layout))
+        extra = None
+        for c0, c1, out_off, bc, mc in layout:
+            list(pool.map(stage, range(c0, c1)))
+            lo = int(starts[c0])
+            hi = int(starts[c1 - 1] + ((lens[c1 - 1] + 3) & ~3))
+            # var-len tables of this chunk, relative to its own first sample / first frame
+            tab = tab_h[4 * c0:4 * c0 + 3 * bc + 1]
+            tab[:bc] = torch.from_numpy(starts[c0:c1] - lo)
+            tab[bc:2 * bc] = torch.from_numpy(lens[c0:c1])
+            tab[2 * bc:3 * bc + 1] = torch.from_numpy((cu[c0:c1 + 1] - cu[c0]).astype(np.int64))
+            tab_dev = tab_d[4 * c0:4 * c0 + 3 * bc + 1]
+            with torch.cuda.stream(copy_stream):
+                if hi > lo:
+                    wave_d[lo:hi].copy_(wave_h[lo:hi], non_blocking=True)
+                tab_dev.copy_(tab, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            stream.wait_event(ev)
+            cu_d = tab_dev[2 * bc:3 * bc + 1].to(torch.int32)
+            max_frames = int(np.diff(cu[c0:c1 + 1]).max())
+            # decode writes straight into this chunk's slab
+            o = out_d[out_off:out_off + 4 * bc + 9 * mc]
+            note_count = o[:4 * bc].view(torch.int32)
+            note_dur = o[4 * bc:4 * bc + 4 * mc].view(torch.int32)
+            note_midi = o[4 * bc + 4 * mc:4 * bc + 8 * mc].view(torch.float32)
+            note_rest = o[4 * bc + 8 * mc:]
+            mel_f32 = torch.empty((mc, 80), dtype=torch.float32, device=dev) if return_intermediates else None
+            self.run_mel(wave_d[lo:], tab_dev[:bc], tab_dev[bc:2 * bc], cu_d, bc, max_frames, mel_f32, ws.units)
+            self.run_trunk(ws, mc, bc, cu_d, max_frames, 'softmax' if quantized else 'sigmoid')
+            self.run_decode(ws, mc, bc, cu_d, note_count, quantized, out=(note_midi, note_dur, note_rest))
+            if return_intermediates:
+                extra = (mel_f32, ws.probs[:mc], ws.bounds[:mc])
+        return out_d[:nbytes_total], cu, layout, extra
+
+    def unpack_slab(self, host: np.ndarray, cu: np.ndarray, layout, extra=None) -> List[Dict[str, np.ndarray]]:
+        """Host copy of a packed note slab -> one dict per clip (input order).  Conversions are done once per chunk on the
+        whole arrays; the per-clip entries are slices."""
+        results: List[Dict[str, np.ndarray]] = []
+        for c0, c1, off, bc, mc in layout:
+            h = host[off:off + 4 * bc + 9 * mc]
+            results.extend(self.unpack(cu[c0:c1 + 1] - cu[c0], h[:4 * bc].view(np.int32),
+                                       h[4 * bc + 4 * mc:4 * bc + 8 * mc].view(np.float32),
+                                       h[4 * bc:4 * bc + 4 * mc].view(np.int32), h[4 * bc + 8 * mc:4 * bc + 9 * mc], extra))
+        return results
 
     def infer(self, waveforms: Sequence[np.ndarray], quantized: bool = False,
               return_intermediates: bool = False) -> List[Dict[str, np.ndarray]]:
         """waveform-in -> notes-out for a list of clips: the batched equivalent of BaseInference.infer
-        (base_infer.py:46-53).  Host buffers in, host buffers out.  The batch is cut into up to 3 chunks of whole
-        clips (small first chunk); for each chunk the clips are staged into pinned memory by a small thread pool (memcpy releases the
-        GIL), copied H2D on a copy stream, and the kernels of the chunk are enqueued behind an event — so staging and
-        H2D of chunk c+1 overlap the kernels of chunk c.  The notes of each chunk come back in ONE packed D2H copy
-        [counts | dur | midi | rest]; there is a single host synchronisation at the end."""
-        b = len(waveforms)
-        if b == 0:
+        (base_infer.py:46-53).  Host buffers in, host buffers out.  The batch is cut into up to 3 chunks of whole clips
+        (small first chunk); for each chunk the clips are staged into pinned memory by a small thread pool (memcpy releases
+        the GIL), copied H2D on a copy stream, and the kernels of the chunk are enqueued behind an event — so staging and
+        H2D of chunk c+1 overlap the kernels of chunk c.  The notes come back in ONE packed D2H copy
+        [counts | dur | midi | rest] per chunk slab; there is a single host synchronisation at the end."""
+        if len(waveforms) == 0:
             return []
-        starts, lens, cu, total = self.tables([int(w.shape[0]) for w in waveforms])
-        m = int(cu[-1])
         dev = self.device
-        chunks = self._chunks(cu) if not return_intermediates else [(0, b)]
         with torch.cuda.device(dev):
-            st = self._staging(total, b, m)
-            stream = torch.cuda.current_stream(dev)
-            if getattr(self, '_copy_stream', None) is None:
-                self._copy_stream = torch.cuda.Stream(dev)
-            copy_stream = self._copy_stream
-            copy_stream.wait_stream(stream)       # previous users of the staging / device buffers are done
-            wave_h, wave_d, tab_h, tab_d, out_h, out_d = (st[k] for k in ('wave_h', 'wave_d', 'tab_h', 'tab_d', 'out_h', 'out_d'))
-            hv = wave_h.numpy()
-            pool = self._pool()
-
-            def stage(i):
-                n = int(lens[i])
-                if n:
-                    hv[starts[i]:starts[i] + n] = waveforms[i]          # dtype cast (if any) + memcpy, GIL released
-
-            ws = self.workspace(max(int(cu[c1] - cu[c0]) for c0, c1 in chunks))
-            extra = None
-            out_off = 0
-            layout = []
-            for c0, c1 in chunks:
-                bc, mc = c1 - c0, int(cu[c1] - cu[c0])
-                list(pool.map(stage, range(c0, c1)))
-                lo = int(starts[c0])
-                hi = int(starts[c1 - 1] + ((lens[c1 - 1] + 3) & ~3))
-                # var-len tables of this chunk, relative to its own first sample / first frame
-                tab = tab_h[4 * c0:4 * c0 + 3 * bc + 1]
-                tab[:bc] = torch.from_numpy(starts[c0:c1] - lo)
-                tab[bc:2 * bc] = torch.from_numpy(lens[c0:c1])
-                tab[2 * bc:3 * bc + 1] = torch.from_numpy((cu[c0:c1 + 1] - cu[c0]).astype(np.int64))
-                tab_dev = tab_d[4 * c0:4 * c0 + 3 * bc + 1]
-                with torch.cuda.stream(copy_stream):
-                    if hi > lo:
-                        wave_d[lo:hi].copy_(wave_h[lo:hi], non_blocking=True)
-                    tab_dev.copy_(tab, non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(copy_stream)
-                stream.wait_event(ev)
-                cu_d = tab_dev[2 * bc:3 * bc + 1].to(torch.int32)
-                max_frames = int(np.diff(cu[c0:c1 + 1]).max())
-                # decode writes straight into this chunk's slab: [counts i32 [bc] | dur i32 [mc] | midi f32 [mc] | rest u8 [mc]]
-                nbytes = 4 * bc + 9 * mc
-                o = out_d[out_off:out_off + nbytes]
-                note_count = o[:4 * bc].view(torch.int32)
-                note_dur = o[4 * bc:4 * bc + 4 * mc].view(torch.int32)
-                note_midi = o[4 * bc + 4 * mc:4 * bc + 8 * mc].view(torch.float32)
-                note_rest = o[4 * bc + 8 * mc:nbytes]
-                mel_f32 = torch.empty((mc, 80), dtype=torch.float32, device=dev) if return_intermediates else None
-                self.run_mel(wave_d[lo:], tab_dev[:bc], tab_dev[bc:2 * bc], cu_d, bc, max_frames, mel_f32, ws.units)
-                self.run_trunk(ws, mc, bc, cu_d, max_frames, 'softmax' if quantized else 'sigmoid')
-                self.run_decode(ws, mc, bc, cu_d, note_count, quantized, out=(note_midi, note_dur, note_rest))
-                out_h[out_off:out_off + nbytes].copy_(o, non_blocking=True)
-                if return_intermediates:
-                    extra = (mel_f32.cpu(), ws.probs[:mc].cpu(), ws.bounds[:mc].cpu())
-                layout.append((c0, c1, out_off, bc, mc))
-                out_off += (nbytes + 15) & ~15
-            stream.synchronize()
-            results: List[Dict[str, np.ndarray]] = []
-            for c0, c1, off, bc, mc in layout:
-                host = out_h[off:off + 4 * bc + 9 * mc].numpy()
-                results.extend(self.unpack(cu[c0:c1 + 1] - cu[c0], host[:4 * bc].view(np.int32),
-                                           host[4 * bc + 4 * mc:4 * bc + 8 * mc].view(np.float32),
-                                           host[4 * bc:4 * bc + 4 * mc].view(np.int32),
-                                           host[4 * bc + 8 * mc:4 * bc + 9 * mc], extra))
-            return results
+            slab, cu, layout, extra = self.enqueue(waveforms, quantized, return_intermediates)
+            out_h = self._stage['out_h']
+            out_h[:slab.numel()].copy_(slab, non_blocking=True)
+            if extra is not None:
+                extra = tuple(t.cpu() for t in extra)
+            torch.cuda.current_stream(dev).synchronize()
+            return self.unpack_slab(out_h[:slab.numel()].numpy(), cu, layout, extra)
 
     def unpack(self, cu, nc, nm, nd, nr, extra=None) -> List[Dict[str, np.ndarray]]:
+        dur_s = nd.astype(np.int64) * self.timestep           # me_infer.py:95 (int64 * python float -> float64), once
+        rest_b = nr.astype(bool)
+        midi = nm.copy()                                     # the pinned staging buffer is reused by the next call
         out = []
         for i in range(len(cu) - 1):
-            r0, n = int(cu[i]), int(nc[i])
-            item = {
-                'note_midi': nm[r0:r0 + n].copy(),
-                'note_dur': nd[r0:r0 + n].astype(np.int64) * self.timestep,     # me_infer.py:95 (int64 * float)
-                'note_rest': nr[r0:r0 + n].astype(bool),
-            }
+            r0 = int(cu[i])
+            r1 = r0 + int(nc[i])
+            item = {'note_midi': midi[r0:r1], 'note_dur': dur_s[r0:r1], 'note_rest': rest_b[r0:r1]}
             if extra is not None:
-                r1 = int(cu[i + 1])
-                item.update(mel=extra[0][r0:r1].numpy(), probs=extra[1][r0:r1].numpy(), bounds=extra[2][r0:r1].numpy())
+                e1 = int(cu[i + 1])
+                item.update(mel=extra[0][r0:e1].numpy(), probs=extra[1][r0:e1].numpy(), bounds=extra[2][r0:e1].numpy())
             out.append(item)
         return out
