@@ -5,17 +5,20 @@
 // output bf16 [M, 512] = 'b h t c -> b t (h c)'.  No head-major copies are made: Q/K/V tiles are TMA boxes cut
 // straight out of qkv.
 //
-// CTA = 128 query rows of one (clip, head), 64-key tiles; 2 CTAs per SM (80 KB smem, 256 TMEM columns each).
-// Roles (256 threads):
-//   warp 0   TMA producer: Q once, then (K_j, V_j) 64-key tiles into a 4-stage ring (128-B swizzle)
-//   warp 1   MMA issuer (one thread):  S_j = Q K_j^T  (tcgen05.mma M128 N64 K16 x4, both operands K-major) into one of
-//            TWO S buffers, so QK_{j+2} is issued as soon as the softmax has consumed S_j and the softmax never waits
-//            for the tensor core in steady state;  O += P_j V_j  (M128 N64 K16 x4, A = P from TENSOR MEMORY, B = V MN-major)
-//   warp 2   TMEM allocator: S0 | S1 | O, 64 fp32 columns each
-//   warps 4-7 softmax, thread = query row: ONE tcgen05.ld of the 64 scores, online softmax in base 2 (ex2.approx), P ->
-//            bf16 pairs -> tcgen05.st over the first half of the S buffer just read.  O stays in TMEM and is rescaled
-//            (tcgen05.ld / st) only when some row maximum of the warp grew by more than 2^8 ("lazy rescale": otherwise
-//            the stale maximum is kept, P <= 256, exact after the final division by the row sum).
+// CTA = 128 query rows of one (clip, head), 64-key tiles; 2 CTAs per SM (82 KB smem, 256 TMEM columns each).
+// The kernel is bound by the MUFU pipe (one ex2 per score: 8192 per tile = 512 clk/SM against 256 clk of tensor work),
+// so the design goal is to keep the four XU pipes fed: TWO independent softmax warpgroups per CTA, each owning every
+// other key tile with its OWN running maximum, row sum and O accumulator (split-K inside the CTA, merged once at the
+// end), so that while one group waits for its PV / next QK^T the other one is exponentiating.
+// Roles (320 threads):
+//   warp 0    TMA producer: Q once, then (K_j, V_j) 64-key tiles into a 4-stage ring (128-B swizzle)
+//   warp 1    MMA issuer (one thread):  S_j = Q K_j^T (tcgen05.mma M128 N64 K16 x4, both operands K-major) into S[j & 1];
+//             O[j & 1] += P_j V_j (M128 N64 K16 x4, A = P from TENSOR MEMORY, B = V MN-major); QK_{j+2} right behind PV_j
+//   warps 2-5 softmax group 0 (even tiles), warps 6-9 group 1 (odd tiles); thread = query row (TMEM lane): online
+//             softmax in base 2 (packed f32x2 scale/sum, ex2.approx), P -> bf16 pairs -> tcgen05.st over the first half of
+//             the S buffer just read.  O stays in TMEM and is rescaled (tcgen05.ld / st) only when some row maximum of
+//             the warp grew by more than 2^8 ("lazy rescale": otherwise the stale maximum is kept, P <= 256, exact after
+//             the final division by the row sum).  warp 2 also owns the TMEM allocation: S0 | S1 | O0 | O1, 64 columns each.
 // Rows of K/V beyond the clip end are masked (p = 0); rows beyond M are zero-filled by TMA.
 #include "host_common.h"
 #include "sm100_ptx.cuh"
@@ -29,7 +32,8 @@ constexpr int TC_BN = 64;                  // keys per tile
 constexpr int TC_QTILE = 128 * 64 * 2;     // 16 KB
 constexpr int TC_KTILE = TC_BN * 64 * 2;   // 8 KB (K or V tile)
 constexpr int TC_STAGES = 4;  // K/V tile j+3 is requested when PV_{j-1} retires: two tile periods to cover the TMA latency
-constexpr int TC_SMEM = TC_QTILE + TC_STAGES * 2 * TC_KTILE + 128 /*barriers*/;
+constexpr int TC_THREADS = 320;
+constexpr int TC_SMEM = TC_QTILE + TC_STAGES * 2 * TC_KTILE + 128 /*barriers*/ + 2 * TC_BM * 8 /*group stats*/;
 constexpr uint32_t TC_TMEM_COLS = 256;
 constexpr uint32_t TC_O_COL = 128;
 
@@ -44,8 +48,27 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// packed f32x2 helpers (sm_100 FFMA2 / FADD2: one issue slot for two lanes of the softmax scale and row sum)
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
 
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_constant__ CUtensorMap tmkv0,
                     const __grid_constant__ CUtensorMap tmq1, const __grid_constant__ CUtensorMap tmkv1,
                     const AttnTcParams p) {
@@ -58,8 +81,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
   uint64_t* kv_empty = bars + 5;   // [4]
   uint64_t* s_full = bars + 9;     // [2]
   uint64_t* p_full = bars + 11;    // [2]
-  uint64_t* pv_done = bars + 13;   // [2], alternating by tile parity
+  uint64_t* all_done = bars + 13;  // every PV retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  float2* stats = reinterpret_cast<float2*>(bars + 16);  // [2][128] (running max, row sum) of each softmax group
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int clip = blockIdx.x / p.tiles_per_clip;
@@ -91,8 +115,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
-      mbar_init(&pv_done[i], 1);
     }
+    mbar_init(all_done, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<TC_TMEM_COLS>(tmem_slot);
@@ -102,7 +126,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(q_full, TC_QTILE);
       tma_load_2d(sQ, tmq, q_full, head * 64, row_begin + q0);
       int s = 0;
@@ -118,7 +142,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16_f32(TC_BM, TC_BN);
       constexpr uint32_t idesc_pv = umma_idesc_bf16_f32(TC_BM, 64, 0, 1);  // B = V is MN-major
       const uint64_t qdesc = umma_desc_kmajor_sw128(smem_u32(sQ));
@@ -143,123 +167,144 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
         const uint32_t p_tmem = tmem_base + (j & 1) * TC_BN;  // P_j (bf16, two keys per column) overwrote S_j's first 32 columns
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // 16 keys per MMA: A +8 TMEM columns, B +16 key rows = 2 KB (+128)
-          umma_bf16_ts(tmem_base + TC_O_COL, p_tmem + 8 * k, vdesc + 128 * k, idesc_pv, (j | k) != 0);
-        umma_commit(&pv_done[j & 1]);
+          umma_bf16_ts(tmem_base + TC_O_COL + (j & 1) * 64, p_tmem + 8 * k, vdesc + 128 * k, idesc_pv, j >= 2 || k != 0);
         umma_commit(&kv_empty[s]);
         // S[j & 1] has been consumed (p_full_j): refill it two tiles ahead so the softmax never waits for the MMAs
         if (j + 2 < n_tiles) issue_qk(j + 2);
       }
+      umma_commit(all_done);
     }
     __syncwarp();
-  } else if (warp >= 4) {
-    const int quad = warp & 3;
-    const int r = quad * 32 + lane;  // query row inside the tile == TMEM lane
+  } else {
+    const int g = (warp - 2) >> 2;  // softmax group: 0 = even key tiles, 1 = odd key tiles
+    const int quad = warp & 3;      // the TMEM lane quadrant this warp may touch
+    const int r = quad * 32 + lane; // query row inside the tile == TMEM lane
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    const uint32_t t_o = t_lane + TC_O_COL;
+    const uint32_t t_s = t_lane + g * TC_BN;
+    const uint32_t t_o = t_lane + TC_O_COL + g * 64;
     const float c = 0.125f * 1.4426950408889634f;  // dim_head^-0.5 * log2(e)
+    const uint64_t c2 = f2_pack(c, c);
     float m_used = -INFINITY, l = 0.f;
-    for (int j = 0; j < n_tiles; ++j) {
+    int it = 0;
+    for (int j = g; j < n_tiles; j += 2, ++it) {
       const int valid = min(TC_BN, T - j * TC_BN);  // keys of this tile inside the clip
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      mbar_wait(&s_full[g], it & 1);  // also: PV_{j-2} (this group's previous tile) has retired, O[g] is quiescent
       tc_fence_after_sync();
-      uint32_t v[64];
-      {
-        uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
-        uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
-        tmem_ld_32x32(t_lane + (j & 1) * TC_BN, lo);
-        tmem_ld_32x32(t_lane + (j & 1) * TC_BN + 32, hi);
-        tmem_ld_wait();
-      }
+      uint32_t v[32];
+      // ---- pass 1: row maximum (the scores are re-read from tensor memory in pass 2: 32 live registers, not 64)
       float mx = -INFINITY;
-      if (valid == TC_BN) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-      } else {
+      for (int h = 0; h < 2; ++h) {
+        tmem_ld_32x32(t_s + 32 * h, v);
+        tmem_ld_wait();
+        if (valid == TC_BN) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (32 * h + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
       }
       // ---- lazy rescale decision (warp-uniform)
       const float m_new = fmaxf(m_used, mx);
-      const bool grow = (j == 0) || ((m_new - m_used) * c > 8.0f);
+      const bool grow = (it == 0) || ((m_new - m_used) * c > 8.0f);
       const bool do_rescale = __any_sync(0xffffffffu, grow);
-      float alpha = 1.0f;
       if (do_rescale) {
-        alpha = (j == 0) ? 0.f : ex2_approx((m_used - m_new) * c);
+        const float alpha = (it == 0) ? 0.f : ex2_approx((m_used - m_new) * c);
         m_used = m_new;
         l *= alpha;
+        if (it > 0) {  // O[g] *= alpha, only when a maximum of this warp moved (rare)
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            tmem_ld_32x32(t_o + 32 * h, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32(t_o + 32 * h, v);
+          }
+          tmem_st_wait();
+        }
       }
       const float mc = m_used * c;
-      // ---- p = 2^(s c - m c), row sum, bf16 pack
+      const uint64_t nmc2 = f2_pack(-mc, -mc);
+      // ---- pass 2: p = 2^(s c - m c), row sum, bf16 pack
       uint32_t pk[32];
-      float rs = 0.f;
-      if (valid == TC_BN) {
+      uint64_t rs_a = f2_pack(0.f, 0.f), rs_b = rs_a;
 #pragma unroll
-        for (int i = 0; i < 64; i += 2) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), c, -mc));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), c, -mc));
-          rs += p0 + p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 64; i += 2) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), c, -mc));
-          float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), c, -mc));
-          if (i >= valid) p0 = 0.f;
-          if (i + 1 >= valid) p1 = 0.f;
-          rs += p0 + p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-        }
-      }
-      l += rs;
-      // ---- O *= alpha, only when a maximum of this warp moved (rare).  PV_{j-1} may still be in flight: wait for it.
-      // pv_done alternates between two barriers so that a parity wait can never be a whole phase behind:
-      // s_full_j implies PV_{j-2} (and its commit) completed, so pv_done[(j-1) & 1] is in the phase of tile j-1 or later.
-      if (do_rescale && j > 0) {
-        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
-        tc_fence_after_sync();
-        uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
-        uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
-        tmem_ld_32x32(t_o, lo);
-        tmem_ld_32x32(t_o + 32, hi);
+      for (int h = 0; h < 2; ++h) {
+        tmem_ld_32x32(t_s + 32 * h, v);
         tmem_ld_wait();
+        if (valid == TC_BN) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-        tmem_st_32x32(t_o, lo);
-        tmem_st_32x32(t_o + 32, hi);
-        tmem_st_wait();
+          for (int i = 0; i < 32; i += 4) {
+            float y0, y1, y2, y3;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), c2, nmc2), y0, y1);
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])), c2, nmc2), y2, y3);
+            const float p0 = ex2_approx(y0), p1 = ex2_approx(y1), p2 = ex2_approx(y2), p3 = ex2_approx(y3);
+            rs_a = f2_add(rs_a, f2_pack(p0, p1));
+            rs_b = f2_add(rs_b, f2_pack(p2, p3));
+            pk[16 * h + (i >> 1)] = pack_bf16x2(p0, p1);
+            pk[16 * h + (i >> 1) + 1] = pack_bf16x2(p2, p3);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), c, -mc));
+            float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), c, -mc));
+            if (32 * h + i >= valid) p0 = 0.f;
+            if (32 * h + i + 1 >= valid) p1 = 0.f;
+            rs_a = f2_add(rs_a, f2_pack(p0, p1));
+            pk[16 * h + (i >> 1)] = pack_bf16x2(p0, p1);
+          }
+        }
       }
-      // ---- P -> TMEM: bf16 pairs into the first 32 columns of this row's S_j (all 64 scores are in registers by now); the
-      //      PV MMA takes its A operand straight from tensor memory, so P never touches shared memory: no 16 KB store, no
-      //      generic->async proxy fence, and the tensor core re-reads 4 KB less smem per MMA.  QK_{j+2} overwrites these
-      //      columns only after PV_j (the MMA pipe executes in issue order).
-      tmem_st_32x32(t_lane + (j & 1) * TC_BN, pk);
+      {
+        float s0, s1, s2, s3;
+        f2_unpack(rs_a, s0, s1);
+        f2_unpack(rs_b, s2, s3);
+        l += (s0 + s1) + (s2 + s3);
+      }
+      // ---- P -> TMEM: bf16 pairs into the first 32 columns of this row's S buffer (all 64 scores have been consumed); the
+      //      PV MMA takes its A operand straight from tensor memory, so P never touches shared memory.  QK_{j+2} overwrites
+      //      these columns only after PV_j (the MMA pipe executes in issue order).
+      tmem_st_32x32(t_s, pk);
       tmem_st_wait();
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[j & 1]);
+      if (lane == 0) mbar_arrive(&p_full[g]);
     }
-    // ---- epilogue: O / l -> bf16 -> out[row, head * 64 ..]
-    mbar_wait(&pv_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
+    // ---- merge the two groups and write O / l -> bf16 -> out[row, head * 64 ..]; group g writes channels [32 g, 32 g + 32)
+    stats[g * TC_BM + r] = make_float2(m_used, l);
+    mbar_wait(all_done, 0);
     tc_fence_after_sync();
-    const float inv = 1.0f / l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float2 sa = stats[r], sb = stats[TC_BM + r];
+    const bool two = n_tiles > 1;
+    const float m = fmaxf(sa.x, sb.x);
+    float wa = ex2_approx((sa.x - m) * c);
+    float wb = two ? ex2_approx((sb.x - m) * c) : 0.f;
+    const float inv = 1.0f / (sa.y * wa + sb.y * wb);
+    wa *= inv;
+    wb *= inv;
     const int qrow = q0 + r;
-    __nv_bfloat16* dst = p.out[grp] + (size_t)(row_begin + qrow) * SOME_DIM + head * 64;
-#pragma unroll 1
-    for (int ch = 0; ch < 2; ++ch) {
-      uint32_t v[32];
-      tmem_ld_32x32(t_o + ch * 32, v);
-      tmem_ld_wait();
-      if (qrow < T) {
+    __nv_bfloat16* dst = p.out[grp] + (size_t)(row_begin + qrow) * SOME_DIM + head * 64 + 32 * g;
+    uint32_t oa[32], ob[32];
+    tmem_ld_32x32(t_lane + TC_O_COL + 32 * g, oa);
+    if (two) tmem_ld_32x32(t_lane + TC_O_COL + 64 + 32 * g, ob);
+    tmem_ld_wait();
+    if (qrow < T) {
+      float o[32];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          reinterpret_cast<uint4*>(dst + ch * 32)[i] =
-              make_uint4(pack_bf16x2(__uint_as_float(v[8 * i]) * inv, __uint_as_float(v[8 * i + 1]) * inv),
-                         pack_bf16x2(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv),
-                         pack_bf16x2(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv),
-                         pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv));
+      for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(oa[i]) * wa;
+      if (two) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = fmaf(__uint_as_float(ob[i]), wb, o[i]);
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        reinterpret_cast<uint4*>(dst)[i] = make_uint4(pack_bf16x2(o[8 * i], o[8 * i + 1]), pack_bf16x2(o[8 * i + 2], o[8 * i + 3]),
+                                                      pack_bf16x2(o[8 * i + 4], o[8 * i + 5]), pack_bf16x2(o[8 * i + 6], o[8 * i + 7]));
     }
     tc_fence_before_sync();
   }
@@ -302,6 +347,6 @@ extern "C" int some_attention_varlen(const some_attn_args* a, cudaStream_t strea
   const long long gx = 1ll * p.tiles_per_clip * a->B;
   SOME_REQUIRE(gx < (1ll << 31), "some_attention_varlen: grid too large");
   dim3 grid(static_cast<unsigned>(gx), SOME_HEADS, a->groups);
-  attention_tc_kernel<<<grid, 256, TC_SMEM, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+  attention_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
   return check_launch("some_attention_varlen");
 }

@@ -28,16 +28,29 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or ~the hint elapses)
-// instead of burning issue slots that the softmax / epilogue warps of the same SM sub-partition need.
+// One lane of a converged warp.  Unlike `lane == 0`, ptxas knows the branch has exactly one active lane, so instructions
+// that take uniform-register operands (UTCHMMA / UTCBAR / UTMALDG) are emitted straight instead of inside an
+// ELECT ... BRA.U.ANY loop over the "possibly many" active lanes (5 extra instructions per MMA on the single issuing thread).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok));
+  return ok != 0;
+}
+// try_wait WITHOUT a suspend-time hint: ptxas emits SYNCS.PHASECHK.TRYWAIT, a hardware-blocking wait that resumes the
+// warp as soon as the phase flips.  (With a hint it becomes PHASECHK + NANOSLEEP.SYNCS, whose wake-up adds latency to every
+// producer -> consumer hand-off: profiles/r01_attention_tc_v6_notes.txt.)
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(200000u)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
 }
