@@ -31,9 +31,10 @@ constexpr int TC_BM = 128;                 // queries per CTA
 constexpr int TC_BN = 64;                  // keys per tile
 constexpr int TC_QTILE = 128 * 64 * 2;     // 16 KB
 constexpr int TC_KTILE = TC_BN * 64 * 2;   // 8 KB (K or V tile)
-constexpr int TC_STAGES = 4;  // K/V tile j+3 is requested when PV_{j-1} retires: two tile periods to cover the TMA latency
+constexpr int TC_STAGES = 5;  // K/V tile j+3 is requested when PV_{j-1} retires: two tile periods to cover the TMA latency
 constexpr int TC_THREADS = 320;
-constexpr int TC_SMEM = TC_QTILE + TC_STAGES * 2 * TC_KTILE + 128 /*barriers*/ + 2 * TC_BM * 8 /*group stats*/;
+constexpr int TC_BAR_BYTES = 256;
+constexpr int TC_SMEM = TC_QTILE + TC_STAGES * 2 * TC_KTILE + TC_BAR_BYTES + 2 * TC_BM * 8 /*group stats*/;
 constexpr uint32_t TC_TMEM_COLS = 256;
 constexpr uint32_t TC_O_COL = 128;
 
@@ -68,6 +69,42 @@ __device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
   return r;
 }
 
+// 2^x for a packed pair on the FMA / ALU pipes instead of the MUFU pipe (the kernel's bottleneck): Cody-Waite split with
+// the 1.5 * 2^23 rounding constant, degree-3 polynomial on [-0.5, 0.5] (max relative error 7.7e-5, well inside the bf16
+// rounding of P), exponent spliced in with an integer add.  TC_POLY_OF_8 of every 8 scores take this path.
+__device__ __forceinline__ void exp2_poly2(uint64_t y2, float& p0, float& p1) {
+  float a, b;
+  f2_unpack(y2, a, b);
+  a = fmaxf(a, -126.f);
+  b = fmaxf(b, -126.f);
+  const uint64_t y = f2_pack(a, b);
+  const uint64_t xf = f2_add(y, f2_pack(12582912.f, 12582912.f));
+  const uint64_t n = f2_add(xf, f2_pack(-12582912.f, -12582912.f));
+  const uint64_t r = f2_fma(n, f2_pack(-1.f, -1.f), y);
+  uint64_t q = f2_fma(f2_pack(0.05508868396282196f, 0.05508868396282196f), r, f2_pack(0.24260404706001282f, 0.24260404706001282f));
+  q = f2_fma(q, r, f2_pack(0.6932762265205383f, 0.6932762265205383f));
+  q = f2_fma(q, r, f2_pack(0.9999289512634277f, 0.9999289512634277f));
+  float qa, qb, xa, xb;
+  f2_unpack(q, qa, qb);
+  f2_unpack(xf, xa, xb);
+  p0 = __int_as_float(__float_as_int(qa) + (__float_as_int(xa) << 23));
+  p1 = __int_as_float(__float_as_int(qb) + (__float_as_int(xb) << 23));
+}
+#ifndef TC_POLY_OF_8
+#define TC_POLY_OF_8 2
+#endif
+
+#ifdef SOME_ATTN_TRACE
+// debug build only (tools/attn_trace.py): SM-clock timestamps of one CTA's softmax groups and MMA thread
+__device__ long long* g_attn_trace = nullptr;
+#define ATTN_TRACE(role, tile, ev)                                                                  \
+  do {                                                                                              \
+    if (trace_on && (tile) < 64) g_attn_trace[(((role) * 64) + (tile)) * 4 + (ev)] = clock64();   \
+  } while (0)
+#else
+#define ATTN_TRACE(role, tile, ev) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(TC_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_constant__ CUtensorMap tmkv0,
                     const __grid_constant__ CUtensorMap tmq1, const __grid_constant__ CUtensorMap tmkv1,
@@ -77,13 +114,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
   uint8_t* sKV = smem + TC_QTILE;                                  // stage s: K at +s * 2 * KTILE, V right after it
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + TC_STAGES * 2 * TC_KTILE);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;    // [4]
-  uint64_t* kv_empty = bars + 5;   // [4]
-  uint64_t* s_full = bars + 9;     // [2]
-  uint64_t* p_full = bars + 11;    // [2]
-  uint64_t* all_done = bars + 13;  // every PV retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
-  float2* stats = reinterpret_cast<float2*>(bars + 16);  // [2][128] (running max, row sum) of each softmax group
+  uint64_t* kv_full = bars + 1;                      // [TC_STAGES]
+  uint64_t* kv_empty = kv_full + TC_STAGES;          // [TC_STAGES]
+  uint64_t* s_full = kv_empty + TC_STAGES;           // [2]
+  uint64_t* p_full = s_full + 2;                     // [2]
+  uint64_t* all_done = p_full + 2;                   // every PV retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(all_done + 1);
+  static_assert(8 * (1 + 2 * TC_STAGES + 6) <= TC_BAR_BYTES, "barrier block too small");
+  float2* stats = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + TC_BAR_BYTES);  // [2][128] (max, row sum) per group
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int clip = blockIdx.x / p.tiles_per_clip;
@@ -97,6 +135,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
   const CUtensorMap* tmq = grp == 0 ? &tmq0 : &tmq1;
   const CUtensorMap* tmkv = grp == 0 ? &tmkv0 : &tmkv1;
   const int n_tiles = (T + TC_BN - 1) / TC_BN;
+#ifdef SOME_ATTN_TRACE
+  const bool trace_on = g_attn_trace != nullptr && blockIdx.x == 7 && blockIdx.y == 3 && blockIdx.z == 0 &&
+                        (lane == 0 || warp == 1) && (warp == 1 || warp == 2 || warp == 6);
+#endif
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) {
@@ -133,6 +175,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
       uint32_t ph = 0;
       for (int j = 0; j < n_tiles; ++j) {
         mbar_wait(&kv_empty[s], ph ^ 1);
+#ifdef SOME_ATTN_SKIPKV  // timing experiment only (wrong results): half of the K/V traffic
+        if (j >= TC_STAGES && (j & 1)) {
+          mbar_arrive(&kv_full[s]);
+          if (++s == TC_STAGES) s = 0, ph ^= 1;
+          continue;
+        }
+#endif
         mbar_arrive_expect_tx(&kv_full[s], 2 * TC_KTILE);
         uint8_t* dst = sKV + s * 2 * TC_KTILE;
         tma_load_2d(dst, tmkv, &kv_full[s], SOME_DIM + head * 64, row_begin + j * TC_BN);
@@ -150,11 +199,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
         const int s = t % TC_STAGES;
         mbar_wait(&kv_full[s], (t / TC_STAGES) & 1);
         tc_fence_after_sync();
+        if (t >= 2) ATTN_TRACE(3, t - 2, 0);
         const uint64_t kdesc = umma_desc_kmajor_sw128(smem_u32(sKV + s * 2 * TC_KTILE));
+        umma_bf16_ss(tmem_base + (t & 1) * TC_BN, qdesc, kdesc, idesc_qk, 0);
+        if (t >= 2) ATTN_TRACE(3, t - 2, 1);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tmem_base + (t & 1) * TC_BN, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+        for (int k = 1; k < 4; ++k)
+          umma_bf16_ss(tmem_base + (t & 1) * TC_BN, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, 1);
+        if (t >= 2) ATTN_TRACE(3, t - 2, 2);
         umma_commit(&s_full[t & 1]);
+        if (t >= 2) ATTN_TRACE(3, t - 2, 3);
       };
       mbar_wait(q_full, 0);
       issue_qk(0);
@@ -163,14 +217,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
         const int s = j % TC_STAGES;
         mbar_wait(&p_full[j & 1], (j >> 1) & 1);  // P_j in smem (and O rescaled if it had to be)
         tc_fence_after_sync();
+        ATTN_TRACE(2, j, 0);
         const uint64_t vdesc = umma_desc_mnmajor_sw128(smem_u32(sKV + s * 2 * TC_KTILE + TC_KTILE), 1024);
         const uint32_t p_tmem = tmem_base + (j & 1) * TC_BN;  // P_j (bf16, two keys per column) overwrote S_j's first 32 columns
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // 16 keys per MMA: A +8 TMEM columns, B +16 key rows = 2 KB (+128)
           umma_bf16_ts(tmem_base + TC_O_COL + (j & 1) * 64, p_tmem + 8 * k, vdesc + 128 * k, idesc_pv, j >= 2 || k != 0);
         umma_commit(&kv_empty[s]);
+        ATTN_TRACE(2, j, 1);
         // S[j & 1] has been consumed (p_full_j): refill it two tiles ahead so the softmax never waits for the MMAs
         if (j + 2 < n_tiles) issue_qk(j + 2);
+        ATTN_TRACE(2, j, 2);
       }
       umma_commit(all_done);
     }
@@ -190,6 +247,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
       const int valid = min(TC_BN, T - j * TC_BN);  // keys of this tile inside the clip
       mbar_wait(&s_full[g], it & 1);  // also: PV_{j-2} (this group's previous tile) has retired, O[g] is quiescent
       tc_fence_after_sync();
+      ATTN_TRACE(g, j, 0);
       uint32_t v[32];
       // ---- pass 1: row maximum (the scores are re-read from tensor memory in pass 2: 32 live registers, not 64)
       float mx = -INFINITY;
@@ -197,15 +255,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
       for (int h = 0; h < 2; ++h) {
         tmem_ld_32x32(t_s + 32 * h, v);
         tmem_ld_wait();
-        if (valid == TC_BN) {
+        if (valid == TC_BN) {  // four independent chains (a single fmax chain is ~16 dependent FMNMX3 per half)
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; i += 8) {
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+            m2 = fmaxf(m2, fmaxf(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])));
+            m3 = fmaxf(m3, fmaxf(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
+          }
+          mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             if (32 * h + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
         }
       }
+      ATTN_TRACE(g, j, 1);
       // ---- lazy rescale decision (warp-uniform)
       const float m_new = fmaxf(m_used, mx);
       const bool grow = (it == 0) || ((m_new - m_used) * c > 8.0f);
@@ -238,10 +304,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
         if (valid == TC_BN) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            float y0, y1, y2, y3;
-            f2_unpack(f2_fma(f2_pack(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), c2, nmc2), y0, y1);
-            f2_unpack(f2_fma(f2_pack(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])), c2, nmc2), y2, y3);
-            const float p0 = ex2_approx(y0), p1 = ex2_approx(y1), p2 = ex2_approx(y2), p3 = ex2_approx(y3);
+            const uint64_t ya = f2_fma(f2_pack(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), c2, nmc2);
+            const uint64_t yb = f2_fma(f2_pack(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])), c2, nmc2);
+            float p0, p1, p2, p3;
+            {
+              float y0, y1;
+              f2_unpack(ya, y0, y1);
+              p0 = ex2_approx(y0);
+              p1 = ex2_approx(y1);
+            }
+            if (TC_POLY_OF_8 >= 4 || ((i & 4) && TC_POLY_OF_8 >= 2)) {  // compile-time after unrolling: pair(s) of every 8 scores
+              exp2_poly2(yb, p2, p3);
+            } else {
+              float y2, y3;
+              f2_unpack(yb, y2, y3);
+              p2 = ex2_approx(y2);
+              p3 = ex2_approx(y3);
+            }
             rs_a = f2_add(rs_a, f2_pack(p0, p1));
             rs_b = f2_add(rs_b, f2_pack(p2, p3));
             pk[16 * h + (i >> 1)] = pack_bf16x2(p0, p1);
@@ -268,11 +347,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
       // ---- P -> TMEM: bf16 pairs into the first 32 columns of this row's S buffer (all 64 scores have been consumed); the
       //      PV MMA takes its A operand straight from tensor memory, so P never touches shared memory.  QK_{j+2} overwrites
       //      these columns only after PV_j (the MMA pipe executes in issue order).
+      ATTN_TRACE(g, j, 2);
       tmem_st_32x32(t_s, pk);
       tmem_st_wait();
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[g]);
+      ATTN_TRACE(g, j, 3);
     }
     // ---- merge the two groups and write O / l -> bf16 -> out[row, head * 64 ..]; group g writes channels [32 g, 32 g + 32)
     stats[g * TC_BM + r] = make_float2(m_used, l);
@@ -318,6 +399,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
 }  // namespace some
 
 using namespace some;
+
+#ifdef SOME_ATTN_TRACE
+extern "C" int some_attention_set_trace(long long* buf) {
+  return cudaMemcpyToSymbol(some::g_attn_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" int some_attention_varlen(const some_attn_args* a, cudaStream_t stream) {
   SOME_REQUIRE(a != nullptr && (a->groups == 1 || a->groups == 2), "some_attention_varlen: bad args");

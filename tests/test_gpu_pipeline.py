@@ -125,6 +125,28 @@ def test_chunked_pipeline_equals_single_chunk(tmp_path):
             np.testing.assert_array_equal(a[k], b[k])
 
 
+def test_pinned_inputs_skip_staging_same_results(tmp_path):
+    """Clips handed over in page-locked memory are copied H2D from the caller's buffer (no staging memcpy); mixed
+    pinned / pageable batches and chunking must give the same notes as the all-pageable path."""
+    from some_b200.engine import pinned_array
+    ins, _ = _plugin('two_head', tmp_path)
+    waves = [synth.synth_waveform(700 + i, seconds=s) for i, s in enumerate([1.3, 0.7, 2.2, 0.4, 1.9])]
+    ref = ins.infer(waves)
+    pinned = []
+    for w in waves:
+        a = pinned_array(len(w))
+        a[:] = w
+        pinned.append(a)
+    assert torch.from_numpy(pinned[0]).is_pinned()
+    mixed = [pinned[0], waves[1], pinned[2], waves[3], pinned[4]]
+    ins.model.MIN_CHUNK_FRAMES = 64
+    for batch in (pinned, mixed):
+        got = ins.infer(batch)
+        for a, b in zip(ref, got):
+            for k in ('note_midi', 'note_dur', 'note_rest'):
+                np.testing.assert_array_equal(a[k], b[k])
+
+
 def test_silence_is_log_clamp(tmp_path):
     ins, _ = _plugin('two_head', tmp_path)
     units = ins.preprocess(np.zeros(44100, dtype=np.float32))['units']

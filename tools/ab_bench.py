@@ -1,0 +1,37 @@
+"""Developer A/B harness: run bench.py against kernel-variant builds of the library (tools/_trace/lib_<name>.so).
+
+  python tools/ab_bench.py build NAME [-DFLAG ...]   # here: rebuilds attention_tc.cu with the flags, links with csrc/build/*.o
+  python tools/ab_bench.py run NAME [bench args]      # on the GPU box: bench.py with that library
+The product never loads these: this script repoints some_b200._lib.LIB_PATH for its own process only."""
+import glob, os, runpy, subprocess, sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent
+CSRC = ROOT / 'some_b200' / 'csrc'
+
+
+def build(name, flags):
+    out = HERE / '_trace'
+    out.mkdir(exist_ok=True)
+    obj = out / f'attention_tc_{name}.o'
+    subprocess.check_call(['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+                           '-Xcompiler', '-fPIC', *flags, '-c', str(CSRC / 'attention_tc.cu'), '-o', str(obj)])
+    objs = [o for o in glob.glob(str(CSRC / 'build' / '*.o')) if not o.endswith('attention_tc.o')]
+    subprocess.check_call(['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', str(out / f'lib_{name}.so'),
+                           str(obj), *objs, '-lcudart'])
+
+
+def run(name, args):
+    sys.path.insert(0, str(ROOT))
+    from some_b200 import _lib
+    _lib.LIB_PATH = HERE / '_trace' / f'lib_{name}.so'
+    sys.argv = ['bench.py', *args]
+    runpy.run_path(str(ROOT / 'bench.py'), run_name='__main__')
+
+
+if __name__ == '__main__':
+    if sys.argv[1] == 'build':
+        build(sys.argv[2], sys.argv[3:])
+    else:
+        run(sys.argv[2], sys.argv[3:])
