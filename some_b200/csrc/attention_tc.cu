@@ -251,24 +251,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
       uint32_t v[32];
       // ---- pass 1: row maximum (the scores are re-read from tensor memory in pass 2: 32 live registers, not 64)
       float mx = -INFINITY;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        tmem_ld_32x32(t_s + 32 * h, v);
+      {
+        uint32_t u[32];
+        tmem_ld_32x32(t_s, v);  // both halves in flight before the single wait
+        tmem_ld_32x32(t_s + 32, u);
         tmem_ld_wait();
-        if (valid == TC_BN) {  // four independent chains (a single fmax chain is ~16 dependent FMNMX3 per half)
+        if (valid == TC_BN) {  // eight independent chains (a single fmax chain is 32 dependent FMNMX3)
           float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+          float m4 = -INFINITY, m5 = -INFINITY, m6 = -INFINITY, m7 = -INFINITY;
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
             m0 = fmaxf(m0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
             m1 = fmaxf(m1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
             m2 = fmaxf(m2, fmaxf(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])));
             m3 = fmaxf(m3, fmaxf(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
+            m4 = fmaxf(m4, fmaxf(__uint_as_float(u[i]), __uint_as_float(u[i + 1])));
+            m5 = fmaxf(m5, fmaxf(__uint_as_float(u[i + 2]), __uint_as_float(u[i + 3])));
+            m6 = fmaxf(m6, fmaxf(__uint_as_float(u[i + 4]), __uint_as_float(u[i + 5])));
+            m7 = fmaxf(m7, fmaxf(__uint_as_float(u[i + 6]), __uint_as_float(u[i + 7])));
           }
-          mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+          mx = fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), fmaxf(fmaxf(m4, m5), fmaxf(m6, m7)));
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (32 * h + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) {
+            if (i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+            if (32 + i < valid) mx = fmaxf(mx, __uint_as_float(u[i]));
+          }
         }
       }
       ATTN_TRACE(g, j, 1);
@@ -297,15 +305,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
       // ---- pass 2: p = 2^(s c - m c), row sum, bf16 pack
       uint32_t pk[32];
       uint64_t rs_a = f2_pack(0.f, 0.f), rs_b = rs_a;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        tmem_ld_32x32(t_s + 32 * h, v);
-        tmem_ld_wait();
+      // 16-column quarters, software-pipelined: the tcgen05.ld of quarter q + 1 is in flight while quarter q is exponentiated
+      auto quarter = [&](const uint32_t(&x)[16], int q) {
         if (valid == TC_BN) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const uint64_t ya = f2_fma(f2_pack(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), c2, nmc2);
-            const uint64_t yb = f2_fma(f2_pack(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])), c2, nmc2);
+          for (int i = 0; i < 16; i += 4) {
+            const uint64_t ya = f2_fma(f2_pack(__uint_as_float(x[i]), __uint_as_float(x[i + 1])), c2, nmc2);
+            const uint64_t yb = f2_fma(f2_pack(__uint_as_float(x[i + 2]), __uint_as_float(x[i + 3])), c2, nmc2);
             float p0, p1, p2, p3;
             {
               float y0, y1;
@@ -323,20 +329,35 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
             }
             rs_a = f2_add(rs_a, f2_pack(p0, p1));
             rs_b = f2_add(rs_b, f2_pack(p2, p3));
-            pk[16 * h + (i >> 1)] = pack_bf16x2(p0, p1);
-            pk[16 * h + (i >> 1) + 1] = pack_bf16x2(p2, p3);
+            pk[8 * q + (i >> 1)] = pack_bf16x2(p0, p1);
+            pk[8 * q + (i >> 1) + 1] = pack_bf16x2(p2, p3);
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), c, -mc));
-            float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), c, -mc));
-            if (32 * h + i >= valid) p0 = 0.f;
-            if (32 * h + i + 1 >= valid) p1 = 0.f;
+          for (int i = 0; i < 16; i += 2) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(x[i]), c, -mc));
+            float p1 = ex2_approx(fmaf(__uint_as_float(x[i + 1]), c, -mc));
+            if (16 * q + i >= valid) p0 = 0.f;
+            if (16 * q + i + 1 >= valid) p1 = 0.f;
             rs_a = f2_add(rs_a, f2_pack(p0, p1));
-            pk[16 * h + (i >> 1)] = pack_bf16x2(p0, p1);
+            pk[8 * q + (i >> 1)] = pack_bf16x2(p0, p1);
           }
         }
+      };
+      {
+        uint32_t xa[16], xb[16];
+        tmem_ld_32x16(t_s, xa);
+        tmem_ld_wait();
+        tmem_ld_32x16(t_s + 16, xb);
+        quarter(xa, 0);
+        tmem_ld_wait();
+        tmem_ld_32x16(t_s + 32, xa);
+        quarter(xb, 1);
+        tmem_ld_wait();
+        tmem_ld_32x16(t_s + 48, xb);
+        quarter(xa, 2);
+        tmem_ld_wait();
+        quarter(xb, 3);
       }
       {
         float s0, s1, s2, s3;
