@@ -168,6 +168,15 @@ typedef struct {
 uint64_t some_decode_scratch_bytes(int M);
 int some_decode_notes(const some_decode_args* args, cudaStream_t stream);
 
+/* ---- K-rms (row §8f-1, the step in front of the path): short-time RMS for the silence slicer.
+ * Replaces get_rms (utils/slicer2.py:5-38) as called by Slicer.slice (slicer2.py:81): zero padding of frame_length / 2 on
+ * both sides, frames of frame_length samples every hop samples, sqrt(mean(x^2)) in float32 with numpy's pairwise summation
+ * order, i.e. BIT-identical to the reference so the host state machine (slicer2.py:84-133) cuts identical chunks.
+ * wave: device f32 [n_samples] (the whole recording, resident; the chunks are later processed in place);
+ * rms: device f32 [n_frames], n_frames = 1 + (n_samples + 2 * (frame_length / 2) - frame_length) / hop. */
+int some_slicer_rms(const float* wave, long long n_samples, int frame_length, int hop, float* rms, int n_frames,
+                    cudaStream_t stream);
+
 /* ---- some_forward: the whole trunk Gmidi_conform.forward (Gconform.py:119-140) + head activation
  * (Gmidi_conform.py:30-40) as one call that enqueues the launch sequence above on `stream`.
  * All pointers are device pointers owned by the caller (packed by some_b200/weights.py); the structs themselves are

@@ -78,6 +78,7 @@ EXPORTS = {
     'some_bound_head': (C.c_int, [_vp, _vp, _vp, _vp, C.c_float, C.c_int, _vp, _vp]),
     'some_decode_scratch_bytes': (C.c_uint64, [C.c_int]),
     'some_decode_notes': (C.c_int, [C.POINTER(DecodeArgs), _vp]),
+    'some_slicer_rms': (C.c_int, [_vp, C.c_longlong, C.c_int, C.c_int, _vp, C.c_int, _vp]),
     'some_forward': (C.c_int, [C.POINTER(ModelC), C.POINTER(WorkspaceC), C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp]),
 }
 

@@ -351,14 +351,28 @@ class Engine:
             off += (4 * bc + 9 * mc + 15) & ~15
         return cu, layout, off
 
-    def enqueue(self, waveforms: Sequence[np.ndarray], quantized: bool = False, return_intermediates: bool = False):
+    def enqueue(self, waveforms: Sequence[np.ndarray], quantized: bool = False, return_intermediates: bool = False,
+                resident=None):
         """Stages, copies and enqueues the whole batch WITHOUT synchronising.  Returns (device slab uint8 [nbytes], cu, layout,
         extra): the decoded notes land in the device slab (see slab_layout); the caller copies it to the host (infer) or
-        hands it to the all-gather (dist.infer_sharded)."""
-        b = len(waveforms)
-        starts, lens, cu, total = self.tables([int(w.shape[0]) for w in waveforms])
-        m = int(cu[-1])
+        hands it to the all-gather (dist.infer_sharded).
+
+        ``resident = (wave_d, ranges)``: the audio is already on the device (f32 tensor) and the clips are the sample ranges
+        ``[(begin, end), ...]`` inside it (``waveforms`` is ignored): no staging, no audio H2D — the slicer path
+        (infer_sliced) cuts the recording where it lies."""
         dev = self.device
+        if resident is not None:
+            wave_res, ranges = resident
+            b = len(ranges)
+            starts = np.asarray([r[0] for r in ranges], dtype=np.int64)
+            lens = np.asarray([r[1] - r[0] for r in ranges], dtype=np.int64)
+            cu = np.zeros(b + 1, dtype=np.int32)
+            np.cumsum(1 + lens // HOP, out=cu[1:])
+            total = 0
+        else:
+            b = len(waveforms)
+            starts, lens, cu, total = self.tables([int(w.shape[0]) for w in waveforms])
+        m = int(cu[-1])
         if return_intermediates:
             layout, nbytes_total = [(0, b, 0, b, m)], (4 * b + 9 * m + 15) & ~15
         else:
@@ -370,28 +384,34 @@ class Engine:
         copy_stream = self._copy_stream
         copy_stream.wait_stream(stream)       # previous users of the staging / device buffers are done
         wave_h, wave_d, tab_h, tab_d, out_d = (st[k] for k in ('wave_h', 'wave_d', 'tab_h', 'tab_d', 'out_d'))
-        hv = wave_h.numpy()
-        pool = self._pool()
+        if resident is not None:
+            wave_d = wave_res
+            direct = []
+        else:
+            hv = wave_h.numpy()
+            pool = self._pool()
 
-        def stage(i):
-            n = int(lens[i])
-            if n:
-                hv[starts[i]:starts[i] + n] = waveforms[i]          # dtype cast (if any) + memcpy, GIL released
+            def stage(i):
+                n = int(lens[i])
+                if n:
+                    hv[starts[i]:starts[i] + n] = waveforms[i]          # dtype cast (if any) + memcpy, GIL released
 
-        # Clips that already live in page-locked memory (pinned_array(), or any float32 view of a pinned torch tensor) are
-        # copied H2D straight from the caller's buffer: no staging memcpy at all.  Everything else goes through the pinned
-        # staging buffer.
-        direct = [bool(lens[i]) and w.dtype == np.float32 and w.flags.c_contiguous and torch.from_numpy(w).is_pinned()
-                  for i, w in enumerate(waveforms)]
+            # Clips that already live in page-locked memory (pinned_array(), or any float32 view of a pinned torch tensor)
+            # are copied H2D straight from the caller's buffer: no staging memcpy at all.  Everything else goes through the
+            # pinned staging buffer.
+            direct = [bool(lens[i]) and w.dtype == np.float32 and w.flags.c_contiguous and torch.from_numpy(w).is_pinned()
+                      for i, w in enumerate(waveforms)]
 
         ws = self.workspace(max(mc for *_, mc in layout))
         extra = None
         for c0, c1, out_off, bc, mc in layout:
-            todo = [i for i in range(c0, c1) if not direct[i]]
-            if todo:
-                list(pool.map(stage, todo))
             lo = int(starts[c0])
-            hi = int(starts[c1 - 1] + ((lens[c1 - 1] + 3) & ~3))
+            todo = []
+            if resident is None:
+                todo = [i for i in range(c0, c1) if not direct[i]]
+                if todo:
+                    list(pool.map(stage, todo))
+                hi = int(starts[c1 - 1] + ((lens[c1 - 1] + 3) & ~3))
             # var-len tables of this chunk, relative to its own first sample / first frame
             tab = tab_h[4 * c0:4 * c0 + 3 * bc + 1]
             tab[:bc] = torch.from_numpy(starts[c0:c1] - lo)
@@ -399,7 +419,9 @@ class Engine:
             tab[2 * bc:3 * bc + 1] = torch.from_numpy((cu[c0:c1 + 1] - cu[c0]).astype(np.int64))
             tab_dev = tab_d[4 * c0:4 * c0 + 3 * bc + 1]
             with torch.cuda.stream(copy_stream):
-                if len(todo) == c1 - c0:
+                if resident is not None:
+                    pass
+                elif len(todo) == c1 - c0:
                     if hi > lo:
                         wave_d[lo:hi].copy_(wave_h[lo:hi], non_blocking=True)
                 else:
@@ -427,6 +449,50 @@ class Engine:
             if return_intermediates:
                 extra = (mel_f32, ws.probs[:mc], ws.bounds[:mc])
         return out_d[:nbytes_total], cu, layout, extra
+
+    def rms_frames(self, wave_d: torch.Tensor, frame_length: int, hop: int) -> np.ndarray:
+        """Short-time RMS of a device-resident f32 waveform (some_slicer_rms), bit-identical to the reference's get_rms
+        (utils/slicer2.py:5-38).  Returns the host copy (one small D2H + sync): the slicer's state machine runs on the host."""
+        n = int(wave_d.numel())
+        n_frames = 1 + (n + 2 * (frame_length // 2) - frame_length) // hop
+        rms_d = torch.empty(n_frames, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.some_slicer_rms(wave_d.data_ptr(), n, frame_length, hop, rms_d.data_ptr(), n_frames, self._stream),
+                   'some_slicer_rms')
+        self.launches += 1
+        return rms_d.cpu().numpy()
+
+    def infer_sliced(self, waveform: np.ndarray, slicer, quantized: bool = False):
+        """One long mono recording -> (chunk offsets in seconds, per-chunk notes): the flow of infer.py:38-41 /
+        batch_infer.py:50-54 (Slicer.slice, then infer on the chunks) with the recording uploaded ONCE.  The RMS frames are
+        computed on the device, the slicer's decisions are taken on the host from the copied RMS list (15 k floats for 5 min),
+        and the chunks are then processed where they lie in device memory as one var-len batch."""
+        from .slicer import chunk_ranges, silence_tags
+        samples = np.ascontiguousarray(waveform, dtype=np.float32)
+        assert samples.ndim == 1, 'infer_sliced expects a mono waveform (infer.py loads with mono=True)'
+        n = int(samples.shape[0])
+        dev = self.device
+        with torch.cuda.device(dev):
+            if (n + slicer.hop_size - 1) // slicer.hop_size <= slicer.min_length:   # slicer2.py:79-80
+                return [0], self.infer([samples], quantized)
+            src = torch.from_numpy(samples)
+            if not src.is_pinned():
+                st = self._staging(n, 1, 1 + n // HOP)
+                st['wave_h'][:n].copy_(src)
+                src = st['wave_h'][:n]
+            wave_d = torch.empty(n, dtype=torch.float32, device=dev)
+            wave_d.copy_(src, non_blocking=True)
+            rms = self.rms_frames(wave_d, slicer.win_size, slicer.hop_size)
+            ranges = chunk_ranges(silence_tags(rms, slicer), rms.shape[0], slicer.hop_size, n)
+            if not ranges:
+                return [], []
+            slab, cu, layout, _ = self.enqueue(None, quantized, resident=(wave_d, ranges))
+            self._staging(0, len(ranges), int(cu[-1]))
+            out_h = self._stage['out_h']
+            out_h[:slab.numel()].copy_(slab, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            results = self.unpack_slab(out_h[:slab.numel()].numpy(), cu, layout)
+        offsets = [begin / slicer.sr for begin, _ in ranges]
+        return offsets, results
 
     def unpack_slab(self, host: np.ndarray, cu: np.ndarray, layout, extra=None) -> List[Dict[str, np.ndarray]]:
         """Host copy of a packed note slab -> one dict per clip (input order).  Conversions are done once per chunk on the
