@@ -461,6 +461,22 @@ class Engine:
         self.launches += 1
         return rms_d.cpu().numpy()
 
+    def rms_frames_many(self, waves_d: Sequence[torch.Tensor], frame_length: int, hop: int) -> List[np.ndarray]:
+        """RMS lists of several device-resident recordings: one launch each into ONE buffer, one D2H copy and sync for all
+        (the dataset driver, some_b200/batch.py)."""
+        counts = [1 + (int(w.numel()) + 2 * (frame_length // 2) - frame_length) // hop for w in waves_d]
+        if not counts:
+            return []
+        cuts = np.zeros(len(counts) + 1, dtype=np.int64)
+        np.cumsum(counts, out=cuts[1:])
+        rms_d = torch.empty(int(cuts[-1]), dtype=torch.float32, device=self.device)
+        for w, a, n in zip(waves_d, cuts, counts):
+            _lib.check(self.lib.some_slicer_rms(w.data_ptr(), int(w.numel()), frame_length, hop, rms_d[a:].data_ptr(), n,
+                                                self._stream), 'some_slicer_rms')
+            self.launches += 1
+        host = rms_d.cpu().numpy()
+        return [host[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+
     def infer_sliced(self, waveform: np.ndarray, slicer, quantized: bool = False):
         """One long mono recording -> (chunk offsets in seconds, per-chunk notes): the flow of infer.py:38-41 /
         batch_infer.py:50-54 (Slicer.slice, then infer on the chunks) with the recording uploaded ONCE.  The RMS frames are
