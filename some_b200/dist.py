@@ -144,3 +144,16 @@ def infer_sharded(plugin, waveforms: Sequence[np.ndarray], group=None) -> List[D
     local = plugin.infer([waveforms[i] for i in shards[rank]])
     dev = getattr(eng, 'device', None) if dist.get_backend(group) == 'nccl' else None
     return gather_results(local, lengths, shards, plugin.timestep, device=dev, group=group)
+
+
+def infer_sliced_sharded(plugin, waveform: np.ndarray, slicer, group=None):
+    """C5 across GPUs: ONE long recording -> slicer -> the chunks sharded over the ranks -> all ranks return
+    (chunk offsets in seconds, notes of every chunk in order).
+
+    Every rank holds the recording and cuts it itself (the device RMS + host run walk cost well under a millisecond of GPU
+    time and are deterministic, so no broadcast of the cut list is needed); the chunks are zero-copy views, each rank stages
+    and uploads only its own shard, and the exchange is the same single all-gather of packed notes as ``infer_sharded``."""
+    ranges = slicer.ranges(waveform)
+    chunks = [waveform[..., a:b] for a, b in ranges]
+    notes = infer_sharded(plugin, chunks, group=group) if chunks else []
+    return [a / slicer.sr for a, _ in ranges], notes

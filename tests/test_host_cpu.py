@@ -198,6 +198,20 @@ def _gloo_worker(rank, world, port, lengths, q):
     waves = [np.zeros(n, dtype=np.float32) for n in lengths]
     merged = sdist.infer_sharded(FakePlugin(), waves)
     ok = all(np.array_equal(m[k], _fake_notes(n)[k]) for m, n in zip(merged, lengths) for k in m)
+
+    # C5 across ranks: one recording, the cuts come from the slicer (here: fixed ranges), the chunks are sharded
+    class FakeSlicer:
+        sr = 44100
+
+        def ranges(self, w):
+            cuts = np.cumsum([0] + lengths)
+            return [(int(a), int(b)) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+
+    rec = np.zeros(int(sum(lengths)), dtype=np.float32)
+    offsets, notes = sdist.infer_sliced_sharded(FakePlugin(), rec, FakeSlicer())
+    kept = [n for n in lengths if n > 0]
+    ok = ok and len(offsets) == len(notes) == len(kept) and offsets[0] == 0.0
+    ok = ok and all(np.array_equal(m[k], _fake_notes(n)[k]) for m, n in zip(notes, kept) for k in m)
     q.put((rank, ok, len(merged)))
     dist.destroy_process_group()
 
