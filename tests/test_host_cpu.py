@@ -242,3 +242,54 @@ def test_inference_package_is_the_drop_in():
     env = dict(os.environ, PYTHONPATH=f'{REPO}:/root/reference')
     out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, cwd='/tmp')
     assert out.returncode == 0 and 'ok' in out.stdout, out.stderr
+
+
+# --------------------------------------------------------------------------- engine host helpers (no GPU: pure numpy)
+def _bare_engine():
+    from some_b200.engine import Engine
+    eng = Engine.__new__(Engine)           # host helpers only: no library, no device
+    eng.timestep = 512 / 44100
+    return eng
+
+
+def test_engine_tables_and_chunk_layout():
+    eng = _bare_engine()
+    rng = np.random.default_rng(3)
+    lens = rng.integers(0, 400000, size=37)
+    lens[5] = 0
+    starts, lens64, cu, total = eng.tables(lens)
+    assert np.all(starts % 4 == 0) and total % 4 == 0                         # 16-byte aligned clip starts (float4 loads)
+    assert np.all(np.diff(starts) >= lens64[:-1]) and total >= starts[-1] + lens64[-1]
+    np.testing.assert_array_equal(np.diff(cu), 1 + lens64 // 512)            # T = 1 + L // hop (spec.py:48-60)
+    chunks = eng._chunks(cu)
+    assert chunks[0][0] == 0 and chunks[-1][1] == len(lens) and len(chunks) <= 3
+    assert all(a[1] == b[0] for a, b in zip(chunks[:-1], chunks[1:])) and all(c1 > c0 for c0, c1 in chunks)
+    frames = [int(cu[c1] - cu[c0]) for c0, c1 in chunks]
+    assert frames[0] == min(frames)                                            # small first chunk gets the GPU going
+    assert eng._chunks(np.asarray([0, 100, 250], dtype=np.int32)) == [(0, 2)]  # small batches are not split
+    cu2, layout, nbytes = eng.slab_layout(lens)
+    np.testing.assert_array_equal(cu2, cu)
+    off = 0
+    for (c0, c1, o, bc, mc), (d0, d1) in zip(layout, chunks):
+        assert (c0, c1, o, bc, mc) == (d0, d1, off, d1 - d0, int(cu[d1] - cu[d0])) and o % 16 == 0
+        off += (4 * bc + 9 * mc + 15) & ~15
+    assert nbytes == off
+
+
+def test_engine_unpack_slab_reads_the_decode_slab_format():
+    """unpack_slab must read exactly the [counts | dur | midi | rest] slab that decode.cu writes and dist.pack_results mirrors."""
+    eng = _bare_engine()
+    lens = [70000, 0, 512 * 40 + 7, 90000, 300]
+    cu, layout, nbytes = eng.slab_layout(lens)
+    notes = [_fake_notes(n) for n in lens]
+    host = np.zeros(nbytes, dtype=np.uint8)
+    for c0, c1, off, bc, mc in layout:
+        frames = [int(cu[i + 1] - cu[i]) for i in range(c0, c1)]
+        slab = sdist.pack_results(notes[c0:c1], frames, 4 * bc + 9 * mc, 512 / 44100)
+        host[off:off + slab.size] = slab
+    back = eng.unpack_slab(host, cu, layout)
+    assert len(back) == len(lens)
+    for a, b in zip(notes, back):
+        assert b['note_midi'].dtype == np.float32 and b['note_dur'].dtype == np.float64 and b['note_rest'].dtype == bool
+        for k in a:
+            np.testing.assert_array_equal(a[k], b[k])
