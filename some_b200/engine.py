@@ -542,16 +542,16 @@ class Engine:
             return self.unpack_slab(out_h[:slab.numel()].numpy(), cu, layout, extra)
 
     def unpack(self, cu, nc, nm, nd, nr, extra=None) -> List[Dict[str, np.ndarray]]:
-        dur_s = nd.astype(np.int64) * self.timestep           # me_infer.py:95 (int64 * python float -> float64), once
+        dur_s = nd * self.timestep     # me_infer.py:95: int64 * python float -> float64; int32 * float gives the same float64s
         rest_b = nr.astype(bool)
         midi = nm.copy()                                     # the pinned staging buffer is reused by the next call
+        first, count = cu[:-1].tolist(), nc.tolist()
+        if extra is None:
+            return [{'note_midi': midi[r0:r0 + n], 'note_dur': dur_s[r0:r0 + n], 'note_rest': rest_b[r0:r0 + n]}
+                    for r0, n in zip(first, count)]
         out = []
-        for i in range(len(cu) - 1):
-            r0 = int(cu[i])
-            r1 = r0 + int(nc[i])
-            item = {'note_midi': midi[r0:r1], 'note_dur': dur_s[r0:r1], 'note_rest': rest_b[r0:r1]}
-            if extra is not None:
-                e1 = int(cu[i + 1])
-                item.update(mel=extra[0][r0:e1].numpy(), probs=extra[1][r0:e1].numpy(), bounds=extra[2][r0:e1].numpy())
-            out.append(item)
+        for i, (r0, n) in enumerate(zip(first, count)):
+            e1 = int(cu[i + 1])
+            out.append({'note_midi': midi[r0:r0 + n], 'note_dur': dur_s[r0:r0 + n], 'note_rest': rest_b[r0:r0 + n],
+                        'mel': extra[0][r0:e1].numpy(), 'probs': extra[1][r0:e1].numpy(), 'bounds': extra[2][r0:e1].numpy()})
         return out
