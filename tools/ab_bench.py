@@ -1,9 +1,11 @@
 """Developer A/B harness: run bench.py against kernel-variant builds of the library (tools/_trace/lib_<name>.so).
 
-  python tools/ab_bench.py build NAME [-DFLAG ...]   # here: rebuilds attention_tc.cu with the flags, links with csrc/build/*.o
+  python tools/ab_bench.py build NAME [--src FILE.cu] [-DFLAG ...]   # here: rebuilds attention_tc.cu (or FILE.cu, which must
+                                                                     # export some_attention_varlen) and links with csrc/build/*.o
   python tools/ab_bench.py run NAME [bench args]      # on the GPU box: bench.py with that library
+  python tools/ab_bench.py pytest NAME [pytest args]  # on the GPU box: the test-suite against that library
 The product never loads these: this script repoints some_b200._lib.LIB_PATH for its own process only."""
-import glob, os, runpy, subprocess, sys
+import glob, os, pathlib, runpy, subprocess, sys
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
@@ -15,8 +17,13 @@ def build(name, flags):
     out = HERE / '_trace'
     out.mkdir(exist_ok=True)
     obj = out / f'attention_tc_{name}.o'
+    src = CSRC / 'attention_tc.cu'
+    if '--src' in flags:
+        i = flags.index('--src')
+        src = pathlib.Path(flags[i + 1]).resolve()
+        flags = flags[:i] + flags[i + 2:]
     subprocess.check_call(['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-                           '-Xcompiler', '-fPIC', *flags, '-c', str(CSRC / 'attention_tc.cu'), '-o', str(obj)])
+                           '-Xcompiler', '-fPIC', *flags, '-c', str(src), '-o', str(obj)])
     objs = [o for o in glob.glob(str(CSRC / 'build' / '*.o')) if not o.endswith('attention_tc.o')]
     subprocess.check_call(['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', str(out / f'lib_{name}.so'),
                            str(obj), *objs, '-lcudart'])
@@ -30,8 +37,19 @@ def run(name, args):
     runpy.run_path(str(ROOT / 'bench.py'), run_name='__main__')
 
 
+def run_pytest(name, args):
+    sys.path.insert(0, str(ROOT))
+    import pytest
+    from some_b200 import _lib
+    _lib.LIB_PATH = HERE / '_trace' / f'lib_{name}.so'
+    os.chdir(ROOT)
+    sys.exit(pytest.main(args or ['tests/test_gpu_kernels.py', 'tests/test_gpu_pipeline.py', '-m', 'gpu', '-x', '-q']))
+
+
 if __name__ == '__main__':
     if sys.argv[1] == 'build':
         build(sys.argv[2], sys.argv[3:])
+    elif sys.argv[1] == 'pytest':
+        run_pytest(sys.argv[2], sys.argv[3:])
     else:
         run(sys.argv[2], sys.argv[3:])
