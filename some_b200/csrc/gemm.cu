@@ -484,11 +484,24 @@ __device__ __forceinline__ void epilogue_warp_staged(const GemmParams& p, const 
 //   producer (warp 0, both CTAs): TMA with .cta_group::2, completion bytes land on the LEADER's full barrier
 //   MMA (warp 1, leader only): tcgen05.mma.cta_group::2 M256 N256 K16; commits are multicast to both CTAs
 //   epilogue (warps 4-11, both CTAs): own 128 TMEM lanes; tmem_empty arrivals go to the leader (remote arrive)
-constexpr int PAIR_STAGES = 5;
 constexpr int PAIR_BN = 256;
 constexpr int PAIR_STAGE_BYTES = BLOCK_M * BLOCK_K * 2 + (PAIR_BN / 2) * BLOCK_K * 2;  // 16 KB A + 16 KB half W
-constexpr int PAIR_EPI_BYTES = EPI_WARPS * 4096;  // one 32 x 128 B transposition tile per epilogue warp
-constexpr int PAIR_SMEM = PAIR_STAGES * PAIR_STAGE_BYTES + PAIR_EPI_BYTES + 1024 + 256;
+// EXPERIMENT (off unless built with -DSOME_GEMM_BULK_RESID, tools/ab_bench.py; not validated on hardware yet): the residual
+// epilogue reads its residual slabs with cp.async.bulk into two extra 4 KB buffers per epilogue warp, one chunk ahead, instead of
+// through registers (the N = K = 512 residual GEMMs sit at ~54 % of the DRAM peak with one 4 KB slab in flight per warp and the
+// kernel at its register cap, profiles/r01_gemm_epilogue_lsu.txt).  It pays for the 64 KB with one pipeline stage.
+#ifdef SOME_GEMM_BULK_RESID
+constexpr bool kBulkResid = true;
+#else
+constexpr bool kBulkResid = false;
+#endif
+template <int EPI>
+struct PairCfg {
+  static constexpr bool BULK = kBulkResid && EPI == SOME_EPI_RESID_F32;
+  static constexpr int STAGES = BULK ? 4 : 5;
+  static constexpr int EPI_BYTES = EPI_WARPS * (BULK ? 3 : 1) * 4096;  // per warp: 32 x 128 B transposition tile (+ 2 residual slabs)
+  static constexpr int SMEM = STAGES * PAIR_STAGE_BYTES + EPI_BYTES + 1024 + 256;
+};
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
@@ -496,13 +509,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                  const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using Cfg = PairCfg<EPI>;
+  constexpr int PAIR_STAGES = Cfg::STAGES;
   uint8_t* epi_stage = smem + PAIR_STAGES * PAIR_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + PAIR_EPI_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + Cfg::EPI_BYTES);
   uint64_t* full_bar = bars;                               // [STAGES]  (used in the leader)
   uint64_t* empty_bar = bars + PAIR_STAGES;                // [STAGES]  (local, multicast commit)
   uint64_t* tmem_full = bars + 2 * PAIR_STAGES;            // [2]       (local, multicast commit)
   uint64_t* tmem_empty = bars + 2 * PAIR_STAGES + 2;       // [2]       (used in the leader)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * PAIR_STAGES + 4);
+  [[maybe_unused]] uint64_t* resid_bar = bars + 2 * PAIR_STAGES + 6;   // [EPI_WARPS][2], bulk-residual experiment only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -532,6 +548,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 2 * EPI_WARPS);
+    }
+    if constexpr (Cfg::BULK) {
+      for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&resid_bar[i], 1);
     }
     fence_mbar_init();
   }
@@ -609,6 +628,33 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     constexpr int COLS_PER_WARP = PAIR_BN / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
+    // ---- bulk-residual experiment: chunk q of this warp (4 chunks of 32 columns per tile, q counts across tiles) lands in
+    //      residual slab q & 1; slab s is re-issued for chunk q + 2 as soon as chunk q has been flushed
+    [[maybe_unused]] uint8_t* rslab = epi_stage + EPI_WARPS * 4096 + ew * 8192;
+    [[maybe_unused]] uint64_t* rbar = resid_bar + 2 * ew;
+    [[maybe_unused]] auto issue_resid = [&](int tile_, int ch, int slab) {
+      if (tile_ >= num_tiles) return;
+      const int grp_ = tile_ / tiles_per_group;
+      const int t_ = tile_ - grp_ * tiles_per_group;
+      const int m_ = t_ / num_n, n_ = t_ - m_ * num_n;
+      const int row0 = m_ * 2 * BLOCK_M + rank * BLOCK_M + quad * 32;
+      const int rows = min(32, max(0, p.M - row0));
+      if (lane == 0) mbar_arrive_expect_tx(&rbar[slab], rows * 128);   // rows == 0: the plain arrival completes the phase
+      __syncwarp();
+      if (lane < rows) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.g[grp_].resid) +
+                             ((size_t)(row0 + lane) * p.ld_out + n_ * PAIR_BN + half * COLS_PER_WARP + ch * 32) * 4;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 128, [%2];" ::"r"(
+                         smem_u32(rslab + slab * 4096 + lane * 128)),
+                     "l"(src), "r"(smem_u32(&rbar[slab]))
+                     : "memory");
+      }
+    };
+    [[maybe_unused]] int q = 0;
+    if constexpr (Cfg::BULK) {
+      issue_resid(pair, 0, 0);
+      issue_resid(pair, 1, 1);
+    }
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int grp = tile / tiles_per_group;
       const int t = tile - grp * tiles_per_group;
@@ -618,7 +664,47 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + acc * PAIR_BN + (static_cast<uint32_t>(quad * 32) << 16);
+      if constexpr (Cfg::BULK) {
+        uint8_t* stage = epi_stage + ew * 4096;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch, ++q) {
+          const int slab = q & 1;
+          const int c = half * COLS_PER_WARP + ch * 32;
+          uint32_t accr[32];
+          tmem_ld_32x32(t_row + c, accr);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(accr[i]);
+          add_bias32(g.bias, n_blk * PAIR_BN + c, v);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<float4*>(stage + stage_off(lane, k)) =
+                make_float4(p.alpha * v[4 * k], p.alpha * v[4 * k + 1], p.alpha * v[4 * k + 2], p.alpha * v[4 * k + 3]);
+          __syncwarp();
+          mbar_wait(&rbar[slab], (q >> 1) & 1);   // the residual slab of this chunk has landed
+          const uint8_t* rs = rslab + slab * 4096;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int row = it * 4 + (lane >> 3), k = lane & 7;
+            if (row_base + row < p.M) {
+              const float4 a = *reinterpret_cast<const float4*>(stage + stage_off(row, k));
+              const float4 r4 = *reinterpret_cast<const float4*>(rs + row * 128 + k * 16);
+              *reinterpret_cast<float4*>(static_cast<uint8_t*>(g.out) +
+                                         ((size_t)(row_base + row) * p.ld_out + n_blk * PAIR_BN + c) * 4 + k * 16) =
+                  make_float4(a.x + r4.x, a.y + r4.y, a.z + r4.z, a.w + r4.w);
+            }
+          }
+          __syncwarp();   // every lane is done with the slab and the transposition tile
+          if (ch + 2 < 4) {
+            issue_resid(tile, ch + 2, slab);
+          } else {
+            issue_resid(tile + num_pairs, ch - 2, slab);
+          }
+        }
+      } else {
       epilogue_warp_staged<EPI>(p, g, row_base, lane, t_row, half * COLS_PER_WARP, n_blk * PAIR_BN, epi_stage + ew * 4096);
+      }
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
@@ -642,15 +728,15 @@ static int launch_gemm_pair(const CUtensorMap* maps, const GemmParams& p, cudaSt
   auto kern = gemm_pair_kernel<EPI>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM);
-    SOME_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(gemm_pair, %d B smem): %s", PAIR_SMEM, cudaGetErrorString(e));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<EPI>::SMEM);
+    SOME_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(gemm_pair, %d B smem): %s", PairCfg<EPI>::SMEM, cudaGetErrorString(e));
     configured = true;
   }
   const int num_m = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   const int tiles = num_m * (p.N / PAIR_BN) * p.groups;
   int pairs = num_sms() / 2;
   if (tiles < pairs) pairs = tiles;
-  kern<<<2 * pairs, GEMM_THREADS, PAIR_SMEM, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+  kern<<<2 * pairs, GEMM_THREADS, PairCfg<EPI>::SMEM, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
   return check_launch("some_gemm(pair)");
 }
 

@@ -1,7 +1,8 @@
 """Developer A/B harness: run bench.py against kernel-variant builds of the library (tools/_trace/lib_<name>.so).
 
-  python tools/ab_bench.py build NAME [--src FILE.cu] [-DFLAG ...]   # here: rebuilds attention_tc.cu (or FILE.cu, which must
-                                                                     # export some_attention_varlen) and links with csrc/build/*.o
+  python tools/ab_bench.py build NAME [--src FILE.cu] [--replace gemm] [-DFLAG ...]
+        # here: rebuilds ONE object with the flags — attention_tc.cu by default, FILE.cu with --src (it must export the same
+        # entry points), or csrc/<X>.cu with --replace X — and links it with the other csrc/build/*.o
   python tools/ab_bench.py run NAME [bench args]      # on the GPU box: bench.py with that library
   python tools/ab_bench.py pytest NAME [pytest args]  # on the GPU box: the test-suite against that library
 The product never loads these: this script repoints some_b200._lib.LIB_PATH for its own process only."""
@@ -16,15 +17,21 @@ CSRC = ROOT / 'some_b200' / 'csrc'
 def build(name, flags):
     out = HERE / '_trace'
     out.mkdir(exist_ok=True)
-    obj = out / f'attention_tc_{name}.o'
+    obj = out / f'variant_{name}.o'
     src = CSRC / 'attention_tc.cu'
+    replaced = 'attention_tc'
+    if '--replace' in flags:
+        i = flags.index('--replace')
+        replaced = flags[i + 1]
+        src = CSRC / f'{replaced}.cu'
+        flags = flags[:i] + flags[i + 2:]
     if '--src' in flags:
         i = flags.index('--src')
         src = pathlib.Path(flags[i + 1]).resolve()
         flags = flags[:i] + flags[i + 2:]
     subprocess.check_call(['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
                            '-Xcompiler', '-fPIC', *flags, '-c', str(src), '-o', str(obj)])
-    objs = [o for o in glob.glob(str(CSRC / 'build' / '*.o')) if not o.endswith('attention_tc.o')]
+    objs = [o for o in glob.glob(str(CSRC / 'build' / '*.o')) if not o.endswith(f'/{replaced}.o')]
     subprocess.check_call(['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', str(out / f'lib_{name}.so'),
                            str(obj), *objs, '-lcudart'])
 
