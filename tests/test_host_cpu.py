@@ -44,6 +44,28 @@ def test_abi_struct_sizes_match_header_layout():
     assert C.sizeof(_lib.DecodeArgs) == 3 * 8 + 4 * 4 + 4 * 4 + 8 * 8
 
 
+def test_abi_struct_layouts_match_the_c_compiler(tmp_path):
+    """sizeof / offsetof from gcc on include/some_b200.h vs the ctypes mirrors (the header is plain C)."""
+    import ctypes as C
+    import shutil
+    from some_b200 import _lib
+    if shutil.which('gcc') is None:
+        pytest.skip('gcc not available')
+    pairs = [('some_gemm_args', _lib.GemmArgs, 'alpha'), ('some_ln_args', _lib.LnArgs, 'M'),
+             ('some_attn_args', _lib.AttnArgs, 'max_frames'), ('some_dwconv_args', _lib.DwconvArgs, 'max_frames'),
+             ('some_decode_args', _lib.DecodeArgs, 'scratch'), ('some_block_weights', _lib.BlockWeightsC, 'b_pw2'),
+             ('some_model', _lib.ModelC, 'b_cut'), ('some_workspace', _lib.WorkspaceC, 'bounds')]
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "some_b200.h"\nint main(void){\n'
+    for name, _, last in pairs:
+        src += f'  printf("%zu %zu\\n", sizeof({name}), offsetof({name}, {last}));\n'
+    src += '  return 0;\n}\n'
+    (tmp_path / 't.c').write_text(src)
+    subprocess.check_call(['gcc', '-I', os.path.join(REPO, 'include'), str(tmp_path / 't.c'), '-o', str(tmp_path / 't')])
+    out = subprocess.check_output([str(tmp_path / 't')], text=True).split()
+    for i, (name, cls, last) in enumerate(pairs):
+        assert (int(out[2 * i]), int(out[2 * i + 1])) == (C.sizeof(cls), getattr(cls, last).offset), name
+
+
 def test_engine_refuses_cpu():
     from some_b200 import _lib, plugin
     cfg = synth.named_config('two_head')
