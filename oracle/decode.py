@@ -89,8 +89,65 @@ def decode_note_sequence(frame2item: np.ndarray, values: np.ndarray, masks: np.n
     return item_values.astype(np.float32), item_dur[1:], item_masks
 
 
+# --------------------------------------------------------------------------- vectorised forms (CPU baseline timing)
+# The loop forms above are the readable specification; they cost ~35 ms per 30 s clip in pure Python, which would inflate
+# the CPU baseline that bench.py reports.  These numpy forms do the same arithmetic in the same order (tests/
+# test_oracle_golden.py::test_vectorised_decode_equals_loops) at the speed of the reference's own torch ops.
+def decode_gaussian_blurred_probs_vec(probs: np.ndarray, vmin, vmax, deviation, threshold):
+    """infer_utils.py:9-24, one gather of the <= 2 * width + 1 bins around the argmax per frame."""
+    probs = np.asarray(probs, dtype=np.float32)
+    t, n = probs.shape
+    interval = (vmax - vmin) / (n - 1)                                 # :11
+    width = int(3 * deviation / interval)                              # :12
+    idx_values = (np.arange(n) * interval + vmin).astype(np.float32)   # :13-14
+    center = probs.argmax(axis=1)                                      # :15
+    win = center[:, None] + np.arange(-width, width + 1)[None, :]      # :16-18 as a window of bin indices
+    ok = (win >= 0) & (win < n)
+    win = np.clip(win, 0, n - 1)
+    w = np.where(ok, np.take_along_axis(probs, win, axis=1), np.float32(0))
+    prod = (w * idx_values[win]).astype(np.float32)
+    product_sum = np.zeros(t, dtype=np.float32)
+    weight_sum = np.zeros(t, dtype=np.float32)
+    for j in range(win.shape[1]):                                      # ascending bins, fp32, like the loop form
+        product_sum = (product_sum + prod[:, j]).astype(np.float32)
+        weight_sum = (weight_sum + w[:, j]).astype(np.float32)
+    values = product_sum / (weight_sum + (weight_sum == 0).astype(np.float32))   # :22
+    rest = probs.max(axis=1) < np.float32(threshold)                   # :23
+    return values.astype(np.float32), rest
+
+
+def decode_note_sequence_vec(frame2item: np.ndarray, values: np.ndarray, masks: np.ndarray, threshold=0.5):
+    """infer_utils.py:42-76 for one clip with bincount / add.at instead of per-frame Python loops."""
+    frame2item = np.asarray(frame2item, dtype=np.int64)
+    masks = np.asarray(masks, dtype=bool)
+    values = np.asarray(values)
+    n_items = int(frame2item.max()) if frame2item.size else 0
+    integer_values = np.issubdtype(values.dtype, np.integer)
+    space = n_items + 1
+    item_dur = np.bincount(frame2item, minlength=space).astype(np.int64)                  # :54-56
+    item_unmasked = np.bincount(frame2item, weights=masks, minlength=space).astype(np.int64)   # :57-59
+    with np.errstate(divide='ignore', invalid='ignore'):
+        item_masks = (item_unmasked[1:] / item_dur[1:]) >= threshold                       # :60
+    vq = np.rint(values).astype(np.int64)                                                  # :61
+    hist = np.bincount(frame2item * 128 + vq, weights=masks, minlength=space * 128).reshape(space, 128)   # :62-64
+    center = hist.argmax(axis=1).astype(np.int64 if integer_values else np.float32)        # :65
+    center[0] = 0                                                                          # :66
+    c = center[frame2item]
+    near = masks & (values >= c - 0.5) & (values <= c + 0.5)                               # :67
+    item_valid = np.bincount(frame2item, weights=near, minlength=space).astype(np.int64)   # :68-70
+    acc_dtype = np.int64 if integer_values else np.float32
+    item_sum = np.zeros(space, dtype=acc_dtype)
+    np.add.at(item_sum, frame2item[near], values[near].astype(acc_dtype))                  # :71-73 frame order, own dtype
+    denom = item_valid[1:] + (item_valid[1:] == 0)
+    if integer_values:
+        item_values = (torch.from_numpy(item_sum[1:]) / torch.from_numpy(denom)).numpy()   # int64 / int64 -> float32 (:74)
+    else:
+        item_values = (item_sum[1:] / denom.astype(np.float32)).astype(np.float32)
+    return item_values.astype(np.float32), item_dur[1:], item_masks
+
+
 # --------------------------------------------------------------------------- plugin restatement
-def infer_clip(sd, config, waveform: np.ndarray, quantized: bool = False, return_intermediates=False):
+def infer_clip(sd, config, waveform: np.ndarray, quantized: bool = False, return_intermediates=False, fast=False):
     """One iteration of BaseInference.infer (base_infer.py:48-52): preprocess (me_infer.py:29-63),
     forward_model (:65-76 / me_quant_infer.py:11-19), postprocess (:78-97 / :21-38)."""
     timestep = config['hop_size'] / config['audio_sample_rate']        # base_infer.py:20
@@ -111,10 +168,11 @@ def infer_clip(sd, config, waveform: np.ndarray, quantized: bool = False, return
         rest = midi == 128                                             # :29
         values = np.clip(midi, 0, 127)                                 # :31
     else:
-        values, rest = decode_gaussian_blurred_probs(                  # me_infer.py:85-88
-            probs_np, config['midi_min'], config['midi_max'],
-            config['midi_prob_deviation'], config['rest_threshold'])
-    note_midi, note_dur, note_mask = decode_note_sequence(frame2item, values, ~rest & masks)   # :89-91
+        blur = decode_gaussian_blurred_probs_vec if fast else decode_gaussian_blurred_probs
+        values, rest = blur(probs_np, config['midi_min'], config['midi_max'],                   # me_infer.py:85-88
+                            config['midi_prob_deviation'], config['rest_threshold'])
+    notes = decode_note_sequence_vec if fast else decode_note_sequence
+    note_midi, note_dur, note_mask = notes(frame2item, values, ~rest & masks)                   # :89-91
     out = {
         'note_midi': note_midi,                                        # :94
         'note_dur': note_dur * timestep,                               # :95 int64 * python float -> float64
@@ -126,6 +184,7 @@ def infer_clip(sd, config, waveform: np.ndarray, quantized: bool = False, return
     return out
 
 
-def infer(sd, config, waveforms, quantized=False):
-    """BaseInference.infer, base_infer.py:46-53 (serial batch-1 loop)."""
-    return [infer_clip(sd, config, w, quantized) for w in waveforms]
+def infer(sd, config, waveforms, quantized=False, fast=False):
+    """BaseInference.infer, base_infer.py:46-53 (serial batch-1 loop).  ``fast`` = the vectorised decode forms (same
+    results, the speed of the reference's torch ops): what bench.py times as the CPU baseline."""
+    return [infer_clip(sd, config, w, quantized, fast=fast) for w in waveforms]

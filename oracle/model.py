@@ -6,10 +6,18 @@ Pinned against the unmodified reference through tests/golden (see oracle/__init_
 
 TEST INFRASTRUCTURE — see oracle/__init__.py.
 """
+import functools
+
 import torch
 import torch.nn.functional as F
 
 from .melbank import mel_filterbank
+
+
+@functools.lru_cache(maxsize=8)
+def _mel_basis(sr, n_fft, n_mels, fmin, fmax):
+    """The reference builds the filterbank once in MelSpectrogram.__init__ (spec.py:22-29), not per clip."""
+    return torch.from_numpy(mel_filterbank(sr, n_fft, n_mels, fmin, fmax)).float()
 
 
 # --------------------------------------------------------------------------- mel front end
@@ -22,7 +30,7 @@ def log_mel(audio: torch.Tensor, sr=44100, n_fft=2048, hop=512, n_mels=80, fmin=
     fft = torch.stft(audio, n_fft=n_fft, hop_length=hop, win_length=n_fft, window=win,
                      center=False, return_complex=True)               # spec.py:52-60
     magnitude = fft.abs()                                             # spec.py:61
-    basis = torch.from_numpy(mel_filterbank(sr, n_fft, n_mels, fmin, fmax)).float()  # spec.py:22-29
+    basis = _mel_basis(sr, n_fft, n_mels, fmin, fmax)                 # spec.py:22-29 (built once)
     mel_output = torch.matmul(basis, magnitude)                       # spec.py:70
     return torch.log(torch.clamp(mel_output, min=clamp))              # spec.py:71
 

@@ -317,3 +317,55 @@ def test_decode_matches_oracle(lib, golden_dir):
         np.testing.assert_allclose(ws.note_midi[r0:r0 + n].cpu().numpy(), nm, rtol=0, atol=1e-4)
         if i < 4:
             np.testing.assert_array_equal(nd, g[f'rnd_note_dur_{i}'])
+
+
+def test_decode_quantized_matches_reference_exactly(lib, golden_dir):
+    """A18, inference/me_quant_infer.py:21-38: argmax over 129 softmax bins, rest = bin 128, values clip(0, 127); the
+    per-note mode / mean run on integers.  Every output of the kernel must equal the oracle AND the reference's own
+    postprocess outputs (tests/golden/decode_quant_kat.npz) exactly, including note_midi (integer sums / counts in fp32)."""
+    from oracle import decode as od
+    from some_b200 import synth
+    from some_b200.engine import Engine, _Workspace
+    g = np.load(golden_dir / 'decode_quant_kat.npz')
+    gen = torch.Generator().manual_seed(77)
+    frames = [700, 700, 1, 37]
+    probs_l, bounds_l = [], []
+    for t in frames:
+        logits = torch.randn(1, t, 129, generator=gen) * 2.0
+        logits[..., 128] += 1.0
+        probs_l.append(torch.softmax(logits, dim=-1)[0])
+        bounds_l.append((torch.rand(1, t, generator=gen) ** 3)[0])
+    probs, bounds = torch.cat(probs_l).contiguous(), torch.cat(bounds_l).contiguous()
+    cu = _cu(frames)
+    m = int(cu[-1])
+    cfg = synth.named_config('quant_two_head')
+    eng = Engine.__new__(Engine)
+    eng.lib, eng.device, eng.config, eng.outdim, eng.launches, eng.prof = lib, torch.device(DEV), cfg, 129, 0, None
+    eng.timestep = 512 / 44100
+    ws = _Workspace(m, 129, DEV)
+    nc = torch.empty(len(frames), dtype=torch.int32, device=DEV)
+    dbg = {}
+    eng.run_decode(ws, m, len(frames), cu, nc, True, dbg, probs=probs.to(DEV), bounds=bounds.to(DEV))
+    torch.cuda.synchronize()
+    cu_h = cu.cpu().numpy()
+    for i, t in enumerate(frames):
+        r0 = int(cu_h[i])
+        p_i, b_i = probs[r0:r0 + t].numpy(), bounds[r0:r0 + t].numpy()
+        midi = p_i.argmax(-1).astype(np.int64)
+        f2i = od.decode_bounds_to_alignment(b_i)
+        np.testing.assert_array_equal(dbg['frame2item'][r0:r0 + t].cpu().numpy(), f2i)
+        np.testing.assert_array_equal(dbg['rest'][r0:r0 + t].cpu().numpy().astype(bool), midi == 128)
+        np.testing.assert_array_equal(dbg['values'][r0:r0 + t].cpu().numpy(), np.clip(midi, 0, 127).astype(np.float32))
+        nm, nd, nk = od.decode_note_sequence(f2i, np.clip(midi, 0, 127), midi != 128)
+        n = int(nc[i])
+        assert n == len(nd) == len(g[f'q{i}_note_midi'])
+        got_midi = ws.note_midi[r0:r0 + n].cpu().numpy()
+        got_dur = ws.note_dur[r0:r0 + n].cpu().numpy()
+        got_rest = ws.note_rest[r0:r0 + n].cpu().numpy().astype(bool)
+        np.testing.assert_array_equal(got_dur, nd)
+        np.testing.assert_array_equal(got_rest, ~nk)
+        np.testing.assert_array_equal(got_midi, nm)
+        # the unmodified reference's outputs for the same inputs
+        np.testing.assert_array_equal(got_midi, g[f'q{i}_note_midi'])
+        np.testing.assert_array_equal(got_dur.astype(np.int64) * (512 / 44100), g[f'q{i}_note_dur'])
+        np.testing.assert_array_equal(got_rest, g[f'q{i}_note_rest'])

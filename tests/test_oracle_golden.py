@@ -7,6 +7,7 @@ import torch
 from oracle import decode as odecode
 from oracle import melbank
 from oracle import model as omodel
+from oracle.metrics import note_agreement
 from some_b200 import synth
 
 
@@ -107,3 +108,69 @@ def test_plugin_restatement_matches_reference(golden_dir, cfg_name):
         np.testing.assert_array_equal(nd * (512 / 44100), g[f'clip{i}_note_dur'])
         np.testing.assert_array_equal(~nk, g[f'clip{i}_note_rest'])
         np.testing.assert_allclose(nm, g[f'clip{i}_note_midi'], rtol=0, atol=1e-4)
+
+
+# --------------------------------------------------------------------------- the benchmarked shapes (round 2)
+@pytest.mark.parametrize('cfg_name', ['two_head', 'quant_two_head', 'midi_conformer'])
+def test_oracle_matches_reference_at_benchmark_lengths(golden_dir, cfg_name):
+    """30 s two_head / quant clips (T = 2584) and a 10 s lay-8 clip: the oracle against outputs of the unmodified reference
+    (tests/golden/make_golden_long.py).  fp32 vs fp32, different thread counts / reduction orders: 2e-5 like the short
+    clips; the decoded notes must be the reference's."""
+    g = np.load(golden_dir / f'long_{cfg_name}.npz')
+    config = synth.named_config(cfg_name)
+    sd = synth.fabricate_state_dict(config, seed=1234)
+    w = synth.synth_waveform(int(g['seed']), seconds=float(g['seconds']))
+    assert len(w) == int(g['num_samples'])
+    quant = cfg_name.startswith('quant')
+    out = odecode.infer_clip(sd, config, w, quantized=quant, return_intermediates=True)
+    assert out['probs'].shape[0] == synth.frames_of(len(w)) == g['bounds'].shape[0]
+    np.testing.assert_allclose(out['bounds'], g['bounds'], rtol=0, atol=5e-5)
+    np.testing.assert_allclose(out['probs'][g['rows']], g['probs_rows'], rtol=0, atol=5e-5)
+    np.testing.assert_allclose(out['probs'].max(1), g['probs_max'], rtol=0, atol=5e-5)
+    ref = {k: g[k] for k in ('note_midi', 'note_dur', 'note_rest')}
+    frames, bounds = note_agreement(ref, out)
+    # cumsum().round() is discontinuous: a 1e-5 difference can move a boundary that sits on a rounding edge
+    assert frames > 0.995 and bounds > 0.995, (frames, bounds)
+    # decode restated on the reference's exact bounds must give the reference's note durations
+    f2i = odecode.decode_bounds_to_alignment(g['bounds'])
+    assert int(f2i.max()) == len(g['note_dur'])
+    np.testing.assert_array_equal(np.bincount(f2i)[1:] * (512 / 44100), g['note_dur'])
+
+
+def test_vectorised_decode_equals_loops():
+    """bench.py times the vectorised decode forms; they must be the loop specification, bit for bit."""
+    gen = torch.Generator().manual_seed(5)
+    for t in (1, 37, 700, 2584):
+        probs = (torch.rand(t, 128, generator=gen) ** 6).numpy()
+        bounds = (torch.rand(t, generator=gen) ** 3).numpy()
+        v0, r0 = odecode.decode_gaussian_blurred_probs(probs, 0, 127, 1.0, 0.1)
+        v1, r1 = odecode.decode_gaussian_blurred_probs_vec(probs, 0, 127, 1.0, 0.1)
+        np.testing.assert_array_equal(v0, v1)
+        np.testing.assert_array_equal(r0, r1)
+        f2i = odecode.decode_bounds_to_alignment(bounds)
+        for vals in (v0, np.clip(probs.argmax(1), 0, 127).astype(np.int64)):
+            a = odecode.decode_note_sequence(f2i, vals, ~r0)
+            b = odecode.decode_note_sequence_vec(f2i, vals, ~r0)
+            for x, y in zip(a, b):
+                assert x.dtype == y.dtype
+                np.testing.assert_array_equal(x, y)
+
+
+def test_quantised_decode_matches_reference(golden_dir):
+    """inference/me_quant_infer.py:21-38 on random 129-bin probabilities: the oracle's quantised decode against the
+    reference's own postprocess outputs (decode_quant_kat.npz), exactly."""
+    g = np.load(golden_dir / 'decode_quant_kat.npz')
+    gen = torch.Generator().manual_seed(77)
+    for i, t in enumerate((700, 700, 1, 37)):
+        logits = torch.randn(1, t, 129, generator=gen) * 2.0
+        logits[..., 128] += 1.0
+        probs = torch.softmax(logits, dim=-1)
+        bounds = torch.rand(1, t, generator=gen) ** 3
+        assert abs(probs.double().sum().item() + bounds.double().sum().item() - float(g[f'q{i}_checksum'])) < 1e-6
+        midi = probs[0].numpy().argmax(-1).astype(np.int64)
+        f2i = odecode.decode_bounds_to_alignment(bounds[0].numpy())
+        for fn in (odecode.decode_note_sequence, odecode.decode_note_sequence_vec):
+            nm, nd, nk = fn(f2i, np.clip(midi, 0, 127), midi != 128)
+            np.testing.assert_array_equal(nm, g[f'q{i}_note_midi'])
+            np.testing.assert_array_equal(nd * (512 / 44100), g[f'q{i}_note_dur'])
+            np.testing.assert_array_equal(~nk, g[f'q{i}_note_rest'])

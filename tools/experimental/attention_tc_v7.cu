@@ -87,8 +87,10 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
-#ifndef TC_POLY_OF_8
-#define TC_POLY_OF_8 2
+// TC_POLY_MASK: bit q set -> the second pair of the q-th group of four scores (q = 0..3 inside every 16) takes the polynomial
+// path: 0b1010 = 2 of 8 scores, 0b1110 = 3 of 8, 0b1111 = 4 of 8, 0 = none.
+#ifndef TC_POLY_MASK
+#define TC_POLY_MASK 0xA
 #endif
 
 #ifdef SOME_ATTN_TRACE
@@ -298,7 +300,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
             p0 = ex2_approx(y0);
             p1 = ex2_approx(y1);
           }
-          if (TC_POLY_OF_8 >= 4 || ((i & 4) && TC_POLY_OF_8 >= 2)) {
+          if ((TC_POLY_MASK >> ((i >> 2) & 3)) & 1) {
             exp2_poly2(yb, p2, p3);
           } else {
             float y2, y3;
