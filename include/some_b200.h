@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SOME_B200_VERSION 100
+#define SOME_B200_VERSION 200
 
 #ifndef __CUDA_RUNTIME_H__
 typedef struct CUstream_st* cudaStream_t;
@@ -40,7 +40,7 @@ typedef struct CUstream_st* cudaStream_t;
 #define SOME_HOP 512
 #define SOME_MEL_BINS 372 /* spectrum bins 0..371 carry all non-zero mel weights (fmax = 8 kHz) */
 #define SOME_MEL_MAXW 24  /* widest mel filter, in bins */
-#define SOME_MEL_TW 1392  /* complex twiddles: radix-4 stage tables 3 x (256 + 64 + 16 + 4), then W_2048^k for k < 372 */
+#define SOME_MEL_TW 1396  /* complex twiddles: W_1024^(n2 k1) at [k1 * 32 + n2] (1024), then W_2048^k for k < 372 */
 
 int some_version(void);
 const char* some_last_error(void);
@@ -50,13 +50,13 @@ const char* some_last_error(void);
  *   wave          f32, all clips in one buffer (clip starts may be padded for 16-byte alignment)
  *   clip_start    int64 [B], first sample of each clip in `wave`;  clip_len int64 [B], samples L_b
  *   cu_frames     int32 [B + 1], T_b = 1 + L_b / 512
- *   max_frames    max_b T_b (grid sizing: ceil(max_frames / 16) CTAs per clip)
+ *   max_frames    max_b T_b (grid sizing: ceil(max_frames / 32) CTAs per clip)
  *   mel_start     int32 [80]: first spectrum bin with non-zero weight in filter m
  *   mel_count     int32 [80]: number of contiguous non-zero bins (<= SOME_MEL_MAXW)
  *   mel_weights   f32 [80][SOME_MEL_MAXW]: those weights (librosa htk / slaney filterbank, spec.py:22-28)
- *   twiddle       f32 [SOME_MEL_TW][2] (cos, sin), host-computed in double: for the radix-4 DIF stages s = 0..3 with
- *                 L = 1024 / 4^s, q = L / 4: exp(-2 pi i m j / L) for m = 1, 2, 3 and j < q (m-major), then
- *                 exp(-2 pi i k / 2048) for k < 372 (real-FFT unpack)
+ *   twiddle       f32 [SOME_MEL_TW][2] (cos, sin), host-computed in double: exp(-2 pi i n2 k1 / 1024) at [k1 * 32 + n2]
+ *                 (between the two 32-point passes of the 32 x 32 FFT), then exp(-2 pi i k / 2048) for k < 372 (real-FFT
+ *                 unpack)
  *   window        f32 [2048] periodic Hann (torch.hann_window)
  *   out_f32       f32 [M, 80] or NULL;  out_bf16  bf16 [M, 80] or NULL (A operand of the input projections) */
 int some_mel_logmel(const float* wave, const int64_t* clip_start, const int64_t* clip_len,
@@ -90,8 +90,19 @@ enum some_epilogue {
   SOME_EPI_GLU_RESID_F32 = 4,  /* out f32 [M,N/2]  = resid + glu(acc + bias)            Gcf glu1/glu2       */
   SOME_EPI_BIAS_F32 = 5,       /* out f32 [M,N]    = acc + bias                         inln/inln1, logits  */
   SOME_EPI_SIGMOID_F32 = 6,    /* out f32 [M,N]    = sigmoid(acc + bias)                outln + sig         */
-  SOME_EPI_SOFTMAX_F32 = 7     /* out f32 [M,N]    = softmax_row(acc + bias), N <= 256  outln + softmax     */
+  SOME_EPI_SOFTMAX_F32 = 7,    /* out f32 [M,N]    = softmax_row(acc + bias), N <= 256  outln + softmax     */
+  /* LayerNorm folded into the GEMMs around it (norm1..norm4 of conform_blocke, Gconform.py:57-62).
+   * Producers: the residual GEMM in front of the LayerNorm also writes bf16(out) and, per row, partial (sum x, sum x^2)
+   * over each 128-column slice of its output.  Consumers: A = bf16(x) (NOT normalised), W' = W * gamma (per column k),
+   * ln_s[n] = sum_k W'[n,k], bias' = bias + W . beta; the epilogue applies  rstd * (acc - mean * ln_s[n]) + bias'[n]
+   * (= LayerNorm(x) . W^T + bias up to rounding) before the activation. */
+  SOME_EPI_LN_STORE_BF16 = 8,      /* consumer of SOME_EPI_STORE_BF16        to_q|to_kv after norm2        */
+  SOME_EPI_LN_SILU_BF16 = 9,       /* consumer of SOME_EPI_SILU_BF16         ffn.ln1 after norm1 / norm4   */
+  SOME_EPI_LN_GLU_BF16 = 10,       /* consumer of SOME_EPI_GLU_BF16          pointwise_conv1 after norm3   */
+  SOME_EPI_RESID_F32_LN = 11,      /* producer variant of SOME_EPI_RESID_F32                               */
+  SOME_EPI_GLU_RESID_F32_LN = 12   /* producer variant of SOME_EPI_GLU_RESID_F32                           */
 };
+#define SOME_LN_SLOTS 8 /* partial-sum slots per row in ln_stats: f32 [M][SOME_LN_SLOTS][2] */
 /* GLU epilogues expect W rows (and bias) packed in 32-row groups: 16 "out" rows followed by their 16
  * "gate" rows (host packing: some_b200/weights.py).  bias arrays are padded to a multiple of 32 floats. */
 typedef struct {
@@ -102,8 +113,25 @@ typedef struct {
   const float* resid[2];
   int groups, M, N, K, lda, ld_out, epilogue;
   float alpha;
+  /* LayerNorm folding (SOME_EPI_LN_* / SOME_EPI_*_LN only; ignored otherwise) */
+  const float* ln_s[2];  /* consumers: f32 [N] column sums of W' (packed like bias) */
+  float* ln_stats[2];    /* producers write, consumers read: f32 [M][SOME_LN_SLOTS][2] partial (sum x, sum x^2) */
+  int ln_parts;          /* consumers: valid slots per row (4 after a RESID producer, 8 after a GLU_RESID one, 1 after
+                            some_row_stats) */
+  uint16_t* out_bf16[2]; /* producers: bf16 [M, ld_out] copy of out (the consumers' A operand) */
 } some_gemm_args;
 int some_gemm(const some_gemm_args* args, cudaStream_t stream);
+
+/* ---- K-rowstats: LayerNorm-producer side for a residual stream no producer GEMM has written (the input projection in
+ * front of block 0, Gconform.py:124-125 -> norm1 at :57): out_bf16 = bf16(x), ln_stats[row][0] = (sum x, sum x^2);
+ * the consumer GEMM then runs with ln_parts = 1. */
+typedef struct {
+  const float* x[2];      /* f32 [M, 512] */
+  uint16_t* out_bf16[2];  /* bf16 [M, 512] */
+  float* ln_stats[2];     /* f32 [M][SOME_LN_SLOTS][2] */
+  int groups, M;
+} some_rowstats_args;
+int some_row_stats(const some_rowstats_args* args, cudaStream_t stream);
 
 /* ---- K-attn: F.scaled_dot_product_attention(q, k, v), no mask, scale 64^-0.5, per clip
  * (base_attention.py:34-45 incl. both rearranges).  qkv bf16 [M, 1536] = [q(8x64) | k(8x64) | v(8x64)]
@@ -141,7 +169,8 @@ int some_bound_head(const float* x, const float* gamma, const float* beta, const
                     float* bounds, cudaStream_t stream);
 
 /* ---- K-decode: utils/infer_utils.py:9-76 + inference/me_infer.py:78-97 (continuous) and
- * inference/me_quant_infer.py:21-38 (quantized: argmax over 129 bins, rest = bin 128), one CTA per clip.
+ * inference/me_quant_infer.py:21-38 (quantized: argmax over 129 bins, rest = bin 128); three launches: frames (grid over all M rows), per-clip
+ * alignment, per-note reduction.  cu_frames must cover rows [0, M).
  *   probs f32 [M, N] (N = 128 sigmoid bins / 129 softmax bins), bounds f32 [M]
  *   outputs are packed per clip at offset cu_frames[b] (a clip never has more notes than frames):
  *     note_midi f32 [M], note_dur i32 [M] (frames; seconds = dur * hop / sr on the host, me_infer.py:95),
@@ -197,6 +226,18 @@ typedef struct {
   const float* b_dw;
   const uint16_t* w_pw2;       /* bf16 [512,512] */
   const float* b_pw2;
+  /* LayerNorm-folded consumers (used when some_model.ln_fold != 0; see SOME_EPI_LN_*): W' = bf16(W * gamma_k),
+   * s[n] = sum_k W'[n,k], b' = bias + W . beta.  norm1 -> ffn1.ln1, norm4 -> ffn2.ln1, norm2 -> to_q|to_kv,
+   * norm3 -> pointwise_conv1 (GLU-packed like w_pw1).  norm5 is never folded (its output is the residual stream). */
+  const uint16_t* ffn_w1f[2];
+  const float* ffn_s1[2];
+  const float* ffn_b1f[2];
+  const uint16_t* w_qkvf;
+  const float* s_qkv;
+  const float* b_qkvf;
+  const uint16_t* w_pw1f;
+  const float* s_pw1;
+  const float* b_pw1f;
 } some_block_weights;
 typedef struct {
   int lay, outdim;
@@ -209,6 +250,8 @@ typedef struct {
   const float* b_head;         /* f32, padded to a multiple of 32 */
   const float* w_cut;          /* cutheard f32 [512] */
   float b_cut;
+  int ln_fold;                 /* != 0: norm1..norm4 folded into the GEMMs around them (needs the *f / s_* fields above and
+                                  some_workspace.xb / ln_stats); 0: stand-alone LayerNorm launches */
 } some_model;
 typedef struct {
   float* x[2];                 /* f32 [M,512] residual streams */
@@ -219,10 +262,51 @@ typedef struct {
   const uint16_t* units;       /* bf16 [M,80] log-mel (input) */
   float* probs;                /* f32 [M,outdim] (output) */
   float* bounds;               /* f32 [M] (output) */
+  uint16_t* xb[2];             /* bf16 [M,512] copy of the residual stream (ln_fold only) */
+  float* ln_stats[2];          /* f32 [M][SOME_LN_SLOTS][2] (ln_fold only) */
 } some_workspace;
-/* head: SOME_EPI_SIGMOID_F32 (sig=True), SOME_EPI_SOFTMAX_F32 (softmax=True) or SOME_EPI_BIAS_F32 (raw logits) */
+/* Optional per-launch timing of some_forward (bench.py's roofline pass): CUDA events on the launching stream around every
+ * kernel the sequencer enqueues.  The library owns the events; read after the stream has been synchronised. */
+typedef struct some_profiler some_profiler;
+enum some_kernel_id {
+  SOME_K_GEMM = 0, SOME_K_ATTENTION = 1, SOME_K_LAYERNORM = 2, SOME_K_DWCONV = 3, SOME_K_BOUND_HEAD = 4, SOME_K_ROW_STATS = 5
+};
+typedef struct {
+  int kernel;   /* enum some_kernel_id */
+  int epilogue; /* GEMM: enum some_epilogue, else 0 */
+  int n, k;     /* GEMM shape (M is the call's), else 0 */
+  float ms;     /* device time between the two events */
+  double work;  /* GEMM: 2 M N K groups FLOP; row-wise kernels: algorithmic bytes; attention: 0 (depends on the clip lengths,
+                   which live on the device: the caller knows them) */
+} some_profile_record;
+int some_profiler_create(int capacity, some_profiler** out);
+int some_profiler_destroy(some_profiler* prof);
+int some_profiler_reset(some_profiler* prof);
+/* Synchronises on the recorded events; fills up to `cap` records in launch order; returns the number recorded (< 0: error). */
+int some_profiler_read(some_profiler* prof, int cap, some_profile_record* out);
+
+/* Optional calibration pass (load time, some_b200/weights.py: bias correction for the bf16 rounding of the weights): while the
+ * sequencer runs on a calibration batch it also computes, for every GEMM, the column means over the M rows of the operand
+ * the rounded weights multiply — A itself, or the normalised rows (x - mean) * rstd for the LayerNorm-folded consumers —
+ * so that the host can add  (W - bf16(W)) . E[a]  to the layer's bias: the rounding of W is a FIXED perturbation of the
+ * model whose mean effect on the outputs would otherwise accumulate in the decoder's boundary cumsum (utils/infer_utils.py:28). */
+#define SOME_CALIB_MAX 512
+#define SOME_CALIB_K 2048
+typedef struct {
+  float* means;   /* device f32 [SOME_CALIB_MAX][2][SOME_CALIB_K] */
+  int count;      /* out: GEMMs recorded (launch order) */
+  const void* w[SOME_CALIB_MAX][2]; /* out: the W pointers of GEMM i (identify the layer; equal for 1-group launches) */
+  int k[SOME_CALIB_MAX];            /* out: its K */
+} some_calibration;
+/* out[k] = mean over rows of a[row, k] (stats == NULL) or of (a[row, k] - mean_row) * rstd_row (row statistics from
+ * ln_stats / parts as in the SOME_EPI_LN_* epilogues).  a bf16 [M, K] with row pitch lda. */
+int some_col_means(const uint16_t* a, int M, int K, int lda, const float* ln_stats, int ln_parts, float* out,
+                   cudaStream_t stream);
+
+/* head: SOME_EPI_SIGMOID_F32 (sig=True), SOME_EPI_SOFTMAX_F32 (softmax=True) or SOME_EPI_BIAS_F32 (raw logits);
+ * prof and calib may be NULL. */
 int some_forward(const some_model* model, const some_workspace* ws, int M, int B, const int32_t* cu_frames,
-                 int max_frames, int head, cudaStream_t stream);
+                 int max_frames, int head, some_profiler* prof, some_calibration* calib, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -234,11 +234,12 @@ extern "C" int some_attention_varlen_mma(const some_attn_args* a, cudaStream_t s
   }
   p.cu_frames = a->cu_frames;
   p.tiles_per_clip = (a->max_frames + ATT_BM - 1) / ATT_BM;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};   // function attributes are per device
+  const int dev_ = device_index();
+  if (!configured[dev_]) {
     cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
     SOME_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
-    configured = true;
+    configured[dev_] = true;
   }
   const long long gx = 1ll * p.tiles_per_clip * a->B;
   SOME_REQUIRE(gx < (1ll << 31), "some_attention_varlen: grid too large");

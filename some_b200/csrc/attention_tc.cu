@@ -49,26 +49,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// packed f32x2 helpers (sm_100 FFMA2 / FADD2: one issue slot for two lanes of the softmax scale and row sum)
-__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-
 // 2^x for a packed pair on the FMA / ALU pipes instead of the MUFU pipe (the kernel's bottleneck): Cody-Waite split with
 // the 1.5 * 2^23 rounding constant, degree-3 polynomial on [-0.5, 0.5] (max relative error 7.7e-5, well inside the bf16
 // rounding of P), exponent spliced in with an integer add.  TC_POLY_OF_8 of every 8 scores take this path.
@@ -195,39 +175,42 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
       constexpr uint32_t idesc_qk = umma_idesc_bf16_f32(TC_BM, TC_BN);
       constexpr uint32_t idesc_pv = umma_idesc_bf16_f32(TC_BM, 64, 0, 1);  // B = V is MN-major
       const uint64_t qdesc = umma_desc_kmajor_sw128(smem_u32(sQ));
-      auto issue_qk = [&](int t) {  // S[t & 1] = Q K_t^T
-        const int s = t % TC_STAGES;
-        mbar_wait(&kv_full[s], (t / TC_STAGES) & 1);
+      // The serial chain between a group's p_full arrival and its next s_full sits on the critical path of that group
+      // (clock64 timeline, profiles/r02_attention_notes.txt), so it is kept as short as possible:
+      //   * the K/V tile of QK_{j+2} is awaited BEFORE the p_full wait (the thread is idle there anyway),
+      //   * PV_j and QK_{j+2} are issued back to back, the commits follow (kv_empty last: nobody waits for it soon).
+      auto wait_kv = [&](int t) {
+        mbar_wait(&kv_full[t % TC_STAGES], (t / TC_STAGES) & 1);
         tc_fence_after_sync();
-        if (t >= 2) ATTN_TRACE(3, t - 2, 0);
+      };
+      auto issue_qk = [&](int t) {  // S[t & 1] = Q K_t^T   (kv_full[t] already awaited)
+        const int s = t % TC_STAGES;
         const uint64_t kdesc = umma_desc_kmajor_sw128(smem_u32(sKV + s * 2 * TC_KTILE));
-        umma_bf16_ss(tmem_base + (t & 1) * TC_BN, qdesc, kdesc, idesc_qk, 0);
-        if (t >= 2) ATTN_TRACE(3, t - 2, 1);
 #pragma unroll
-        for (int k = 1; k < 4; ++k)
-          umma_bf16_ss(tmem_base + (t & 1) * TC_BN, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, 1);
-        if (t >= 2) ATTN_TRACE(3, t - 2, 2);
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tmem_base + (t & 1) * TC_BN, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
         umma_commit(&s_full[t & 1]);
-        if (t >= 2) ATTN_TRACE(3, t - 2, 3);
       };
       mbar_wait(q_full, 0);
+      wait_kv(0);
       issue_qk(0);
-      if (n_tiles > 1) issue_qk(1);
+      if (n_tiles > 1) {
+        wait_kv(1);
+        issue_qk(1);
+      }
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j % TC_STAGES;
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);  // P_j in smem (and O rescaled if it had to be)
+        if (j + 2 < n_tiles) wait_kv(j + 2);      // off the critical path: before the p_full wait
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);  // P_j in tensor memory (and O rescaled if it had to be)
         tc_fence_after_sync();
-        ATTN_TRACE(2, j, 0);
         const uint64_t vdesc = umma_desc_mnmajor_sw128(smem_u32(sKV + s * 2 * TC_KTILE + TC_KTILE), 1024);
         const uint32_t p_tmem = tmem_base + (j & 1) * TC_BN;  // P_j (bf16, two keys per column) overwrote S_j's first 32 columns
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // 16 keys per MMA: A +8 TMEM columns, B +16 key rows = 2 KB (+128)
           umma_bf16_ts(tmem_base + TC_O_COL + (j & 1) * 64, p_tmem + 8 * k, vdesc + 128 * k, idesc_pv, j >= 2 || k != 0);
-        umma_commit(&kv_empty[s]);
-        ATTN_TRACE(2, j, 1);
-        // S[j & 1] has been consumed (p_full_j): refill it two tiles ahead so the softmax never waits for the MMAs
+        // S[j & 1] has been consumed (p_full_j): refill it two tiles ahead, right behind PV_j on the in-order tensor pipe
         if (j + 2 < n_tiles) issue_qk(j + 2);
-        ATTN_TRACE(2, j, 2);
+        umma_commit(&kv_empty[s]);
       }
       umma_commit(all_done);
     }
@@ -442,15 +425,16 @@ extern "C" int some_attention_varlen(const some_attn_args* a, cudaStream_t strea
   }
   p.cu_frames = a->cu_frames;
   p.tiles_per_clip = (a->max_frames + TC_BM - 1) / TC_BM;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};   // function attributes are per device
+  const int dev_ = device_index();
+  if (!configured[dev_]) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     SOME_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(attention_tc): %s", cudaGetErrorString(e));
     // two CTAs per SM need the full shared-memory carveout (2 x 113 KB)
     e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     SOME_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(attention_tc carveout): %s", cudaGetErrorString(e));
-    configured = true;
+    configured[dev_] = true;
   }
   const long long gx = 1ll * p.tiles_per_clip * a->B;
   SOME_REQUIRE(gx < (1ll << 31), "some_attention_varlen: grid too large");

@@ -1,17 +1,19 @@
-// K-decode: probabilities -> notes, one CTA per clip.  Restates utils/infer_utils.py:9-76 and the
-// postprocess glue of inference/me_infer.py:78-97 / inference/me_quant_infer.py:21-38 (masks are all
-// ones on the inference path, me_infer.py:62, so the mask multiplications are identities).
+// K-decode: probabilities -> notes.  Restates utils/infer_utils.py:9-76 and the postprocess glue of
+// inference/me_infer.py:78-97 / inference/me_quant_infer.py:21-38 (masks are all ones on the inference path,
+// me_infer.py:62, so the mask multiplications are identities).  Three launches per call:
 //
-//   phase A  per frame (warp per frame): argmax over the N pitch bins; continuous: weighted mean of the
-//            bin values over [c-3, c+3] (infer_utils.py:11-22), rest = max < threshold (:23);
-//            quantized: value = clip(argmax, 0, 127), rest = argmax == 128 (me_quant_infer.py:28-31)
-//   phase B  boundary alignment (infer_utils.py:27-39): cumsum().round().long(), diff(prepend -1) > 0,
-//            cumsum.  The float cumsum is the only order-sensitive step: ATen's CPU kernel accumulates
-//            sequentially in double and rounds every prefix to float, so one thread does exactly that
-//            (a chain of T DADDs, ~10 us for 30 s); everything after it is integer and runs as a block scan.
-//   phase C  per note (warp per note; notes are contiguous frame ranges, so no atomics on global memory):
-//            duration, unmasked duration, 128-bin histogram of round(value) -> mode (first maximal bin),
-//            sequential fp32 sum of the values within +-0.5 of the mode (CPU scatter_add order), mean.
+//   phase A  decode_frames_kernel, grid over ALL frames (warp per frame): argmax over the N pitch bins; continuous:
+//            weighted mean of the bin values over [c-3, c+3] (infer_utils.py:11-22), rest = max < threshold (:23);
+//            quantized: value = clip(argmax, 0, 127), rest = argmax == 128 (me_quant_infer.py:28-31).  This is the only
+//            phase that touches the [M, N] probabilities (HBM-bound stream).
+//   phase B  decode_align_kernel, one CTA per clip: boundary alignment (infer_utils.py:27-39): cumsum().round().long(),
+//            diff(prepend -1) > 0, cumsum.  The float cumsum is the only order-sensitive step: ATen's CPU kernel accumulates
+//            sequentially in double and rounds every prefix to float, so one thread does exactly that (a chain of T DADDs,
+//            ~15 us for 30 s, all clips in parallel); everything after it is integer and runs as a block scan.
+//   phase C  decode_notes_kernel, DEC_NOTE_CTAS CTAs per clip (warp per note; notes are contiguous frame ranges, so no
+//            atomics on global memory): duration, unmasked duration, 128-bin histogram of round(value) -> mode (first
+//            maximal bin), sequential fp32 sum of the values within +-0.5 of the mode (CPU scatter_add order), mean.
+// (Round 1 ran all three phases in ONE CTA per clip: 64 CTAs on 148 SMs, 0.65 ms per 64 x 30 s batch, 2 % of the HBM rate.)
 // Outputs are packed per clip at offset cu_frames[b] (a clip never has more notes than frames).
 #include "host_common.h"
 #include "sm100_ptx.cuh"
@@ -42,11 +44,55 @@ struct DecParams {
   int32_t* note_start;  // [M]
 };
 
-__global__ void __launch_bounds__(DEC_THREADS) decode_kernel(const DecParams p) {
-  __shared__ float s_f[DEC_CHUNK];
+constexpr int DEC_NOTE_CTAS = 16;   // CTAs per clip in phase C
+
+// ---------------------------------------------------------------- phase A: per-frame pitch value / rest
+__global__ void __launch_bounds__(DEC_THREADS) decode_frames_kernel(const DecParams p, int M) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (DEC_THREADS / 32) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int N = p.N;
+  const float* __restrict__ pr = p.probs + (size_t)row * N;
+  float best = -INFINITY;
+  int bidx = 0x7fffffff;
+  for (int j = lane; j < N; j += 32) {
+    const float v = pr[j];
+    if (v > best) best = v, bidx = j;  // ascending j: keeps the first maximum of this lane
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    if (ov > best || (ov == best && oi < bidx)) best = ov, bidx = oi;
+  }
+  float value;
+  bool is_rest;
+  if (p.quantized) {
+    is_rest = (bidx == 128);
+    value = static_cast<float>(min(max(bidx, 0), 127));
+  } else {
+    const int lo = max(bidx - p.width, 0), hi = min(bidx + p.width + 1, N);
+    float ps = 0.f, ws = 0.f;
+    for (int j = lo; j < hi; ++j) {  // <= 7 terms, ascending (all lanes compute the same sums)
+      const float w = pr[j];
+      // explicit roundings (no FMA contraction): product and sums are separate fp32 ops in the reference
+      ps = __fadd_rn(ps, __fmul_rn(w, __fadd_rn(__fmul_rn(static_cast<float>(j), p.interval), p.vmin)));
+      ws = __fadd_rn(ws, w);
+    }
+    value = ps / (ws + (ws == 0.f ? 1.f : 0.f));
+    is_rest = best < p.threshold;
+  }
+  if (lane == 0) {
+    p.values[row] = value;
+    p.rest[row] = is_rest ? 1 : 0;
+  }
+}
+
+// ---------------------------------------------------------------- phase B: frame -> note index
+__global__ void __launch_bounds__(DEC_THREADS) decode_align_kernel(const DecParams p) {
+  __shared__ __align__(16) float s_f[DEC_CHUNK];
   __shared__ int s_i[DEC_CHUNK];
   __shared__ int s_warp[DEC_THREADS / 32];
-  __shared__ int s_hist[DEC_THREADS / 32][128];
   __shared__ int s_carry;
   __shared__ double s_acc;
   __shared__ int s_prev_step;
@@ -55,52 +101,10 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(const DecParams p) 
   const int row0 = p.cu_frames[clip];
   const int T = p.cu_frames[clip + 1] - row0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = DEC_THREADS / 32;
   if (T <= 0) {
     if (tid == 0) p.note_count[clip] = 0;
     return;
   }
-  const int N = p.N;
-
-  // ---------------------------------------------------------------- phase A: per-frame pitch value / rest
-  for (int f = warp; f < T; f += NW) {
-    const float* __restrict__ pr = p.probs + (size_t)(row0 + f) * N;
-    float best = -INFINITY;
-    int bidx = 0x7fffffff;
-    for (int j = lane; j < N; j += 32) {
-      const float v = pr[j];
-      if (v > best) best = v, bidx = j;  // ascending j: keeps the first maximum of this lane
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-      if (ov > best || (ov == best && oi < bidx)) best = ov, bidx = oi;
-    }
-    float value;
-    bool is_rest;
-    if (p.quantized) {
-      is_rest = (bidx == 128);
-      value = static_cast<float>(min(max(bidx, 0), 127));
-    } else {
-      const int lo = max(bidx - p.width, 0), hi = min(bidx + p.width + 1, N);
-      float ps = 0.f, ws = 0.f;
-      for (int j = lo; j < hi; ++j) {  // <= 7 terms, ascending (all lanes compute the same sums)
-        const float w = pr[j];
-        // explicit roundings (no FMA contraction): product and sums are separate fp32 ops in the reference
-        ps = __fadd_rn(ps, __fmul_rn(w, __fadd_rn(__fmul_rn(static_cast<float>(j), p.interval), p.vmin)));
-        ws = __fadd_rn(ws, w);
-      }
-      value = ps / (ws + (ws == 0.f ? 1.f : 0.f));
-      is_rest = best < p.threshold;
-    }
-    if (lane == 0) {
-      p.values[row0 + f] = value;
-      p.rest[row0 + f] = is_rest ? 1 : 0;
-    }
-  }
-
-  // ---------------------------------------------------------------- phase B: frame -> note index
   if (tid == 0) {
     s_acc = 0.0;
     s_prev_step = -1;
@@ -113,9 +117,20 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(const DecParams p) 
     __syncthreads();
     if (tid == 0) {
       double acc = s_acc;
-      for (int i = 0; i < n; ++i) {
+      int i = 0;
+      // the DADD chain is the critical path; loads / conversions / stores of four frames are batched around it
+      for (; i + 4 <= n; i += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(&s_f[i]);
+        float4 o;
+        acc += static_cast<double>(v.x), o.x = static_cast<float>(acc);  // prefix rounded to float, like ATen's CPU cumsum
+        acc += static_cast<double>(v.y), o.y = static_cast<float>(acc);
+        acc += static_cast<double>(v.z), o.z = static_cast<float>(acc);
+        acc += static_cast<double>(v.w), o.w = static_cast<float>(acc);
+        *reinterpret_cast<float4*>(&s_f[i]) = o;
+      }
+      for (; i < n; ++i) {
         acc += static_cast<double>(s_f[i]);
-        s_f[i] = static_cast<float>(acc);  // prefix rounded to float, like ATen's CPU cumsum
+        s_f[i] = static_cast<float>(acc);
       }
       s_acc = acc;
     }
@@ -166,13 +181,20 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(const DecParams p) 
     }
     __syncthreads();
   }
-  const int num_notes = s_carry;
-  if (tid == 0) p.note_count[clip] = num_notes;
-  __threadfence_block();
-  __syncthreads();
+  if (tid == 0) p.note_count[clip] = s_carry;
+}
 
-  // ---------------------------------------------------------------- phase C: per-note reduction
-  for (int nt = warp; nt < num_notes; nt += NW) {
+// ---------------------------------------------------------------- phase C: per-note reduction
+__global__ void __launch_bounds__(DEC_THREADS) decode_notes_kernel(const DecParams p) {
+  __shared__ int s_hist[DEC_THREADS / 32][128];
+  const int clip = blockIdx.y;
+  const int row0 = p.cu_frames[clip];
+  const int T = p.cu_frames[clip + 1] - row0;
+  if (T <= 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = DEC_THREADS / 32;
+  const int num_notes = p.note_count[clip];
+  for (int nt = blockIdx.x * NW + warp; nt < num_notes; nt += gridDim.x * NW) {
     const int start = p.note_start[row0 + nt];
     const int end = (nt + 1 < num_notes) ? p.note_start[row0 + nt + 1] : T;
     const int dur = end - start;
@@ -252,6 +274,9 @@ extern "C" int some_decode_notes(const some_decode_args* a, cudaStream_t stream)
   p.values = a->dbg_values ? a->dbg_values : reinterpret_cast<float*>(s + 4 * M);
   p.note_start = reinterpret_cast<int32_t*>(s + 8 * M);
   p.rest = a->dbg_rest ? a->dbg_rest : (s + 12 * M);
-  decode_kernel<<<a->B, DEC_THREADS, 0, stream>>>(p);
+  SOME_REQUIRE(a->M > 0, "some_decode_notes: M must be positive (got %d)", a->M);
+  decode_frames_kernel<<<(a->M + DEC_THREADS / 32 - 1) / (DEC_THREADS / 32), DEC_THREADS, 0, stream>>>(p, a->M);
+  decode_align_kernel<<<a->B, DEC_THREADS, 0, stream>>>(p);
+  decode_notes_kernel<<<dim3(DEC_NOTE_CTAS, a->B), DEC_THREADS, 0, stream>>>(p);
   return check_launch("some_decode_notes");
 }

@@ -17,6 +17,8 @@
 #include "host_common.h"
 #include "sm100_ptx.cuh"
 
+#include <string.h>
+
 #include "../../include/some_b200.h"
 
 namespace some {
@@ -32,6 +34,8 @@ struct GemmGroup {
   const float* bias;   // [N] in packed-column order, or nullptr
   void* out;           // bf16 or f32, row pitch ld_out elements
   const float* resid;  // f32 [M, ld_out] or nullptr (may alias out)
+  const float* ln_s;   // LayerNorm-folded consumers: column sums of W' [N]
+  float* ln_stats;     // f32 [M][SOME_LN_SLOTS][2] partial (sum x, sum x^2): written by producers, read by consumers
 };
 
 struct GemmParams {
@@ -39,6 +43,7 @@ struct GemmParams {
   int groups;
   int ld_out;
   int n_valid;  // softmax / sigmoid heads: number of real columns
+  int ln_parts; // LayerNorm-folded consumers: valid slots per row of ln_stats
   float alpha;
   GemmGroup g[2];
 };
@@ -336,29 +341,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
 // fully coalesced 128-byte rows: lane -> (row = 4 it + lane / 8, 16-byte chunk = lane % 8).
 __device__ __forceinline__ uint32_t stage_off(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
-template <bool kResid>
 __device__ __forceinline__ void stage_flush(const GemmParams& p, const GemmGroup& g, int row_base, int lane,
-                                            const uint8_t* stage, size_t col_byte, int elem_bytes, const float4 (&rp)[8]) {
+                                            const uint8_t* stage, size_t col_byte) {
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int row = it * 4 + (lane >> 3), ch = lane & 7;
-    float4 v = *reinterpret_cast<const float4*>(stage + stage_off(row, ch));
-    if (row_base + row < p.M) {
-      if constexpr (kResid) v = make_float4(v.x + rp[it].x, v.y + rp[it].y, v.z + rp[it].z, v.w + rp[it].w);
-      uint8_t* dst = static_cast<uint8_t*>(g.out) + (size_t)(row_base + row) * p.ld_out * elem_bytes + col_byte + ch * 16;
-      *reinterpret_cast<float4*>(dst) = v;
-    }
-  }
-}
-__device__ __forceinline__ void resid_prefetch(const GemmParams& p, const GemmGroup& g, int row_base, int lane,
-                                               size_t col_byte, float4 (&rp)[8]) {
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int row = it * 4 + (lane >> 3), ch = lane & 7;
-    rp[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 v = *reinterpret_cast<const float4*>(stage + stage_off(row, ch));
     if (row_base + row < p.M)
-      rp[it] = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(g.resid) +
-                                                (size_t)(row_base + row) * p.ld_out * 4 + col_byte + ch * 16);
+      *reinterpret_cast<float4*>(static_cast<uint8_t*>(g.out) + (size_t)(row_base + row) * p.ld_out * 2 + col_byte + ch * 16) = v;
   }
 }
 __device__ __forceinline__ void add_bias32(const float* bias, int col, float (&v)[32]) {
@@ -370,14 +360,76 @@ __device__ __forceinline__ void add_bias32(const float* bias, int col, float (&v
     v[4 * i + 0] += b.x, v[4 * i + 1] += b.y, v[4 * i + 2] += b.z, v[4 * i + 3] += b.w;
   }
 }
+__device__ __forceinline__ uint64_t u2_pair(uint32_t lo, uint32_t hi) {   // two accumulator registers as one packed f32x2
+  return f2_pack(__uint_as_float(lo), __uint_as_float(hi));
+}
+// 32 accumulator columns of this thread's row -> 16 packed pairs with the bias (or the folded LayerNorm) applied.
+// LayerNorm folded into the consumer GEMM (Gconform.py:57-62: ffn(norm(x)), att(norm(x)), conv(norm(x))): the accumulator
+// was taken over bf16(x) and W' = W * gamma, so   LN(x) . W^T + bias = rstd * (acc - mean * s_n) + bias'_n   with
+// s_n = sum_k W'[n,k] (ln_s) and bias' = bias + W . beta (passed as bias).  ra2 = (rstd, rstd), nmu2 = (-mean, -mean) of
+// THIS thread's row.  Everything on the packed f32x2 pipes: 2 FFMA2 per pair (the plain bias add is 1 FADD2).
+template <bool kLn>
+__device__ __forceinline__ void bias_or_ln32(const GemmGroup& g, int col, const uint32_t (&acc)[32], uint64_t (&v)[16],
+                                             uint64_t ra2, uint64_t nmu2) {
+  if constexpr (!kLn) {
+    if (g.bias == nullptr) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = u2_pair(acc[2 * i], acc[2 * i + 1]);
+    } else {
+      const float4* b4 = reinterpret_cast<const float4*>(g.bias + col);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = __ldg(b4 + i);
+        v[2 * i] = f2_add(u2_pair(acc[4 * i], acc[4 * i + 1]), f2_pack(b.x, b.y));
+        v[2 * i + 1] = f2_add(u2_pair(acc[4 * i + 2], acc[4 * i + 3]), f2_pack(b.z, b.w));
+      }
+    }
+  } else {
+    const float4* b4 = reinterpret_cast<const float4*>(g.bias + col);
+    const float4* s4 = reinterpret_cast<const float4*>(g.ln_s + col);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#ifdef SOME_DIAG_LNC_NOS       // timing experiment only (wrong results)
+      const float4 b = __ldg(b4 + i), s = b;
+#else
+      const float4 b = __ldg(b4 + i), s = __ldg(s4 + i);
+#endif
+      v[2 * i] = f2_fma(f2_fma(f2_pack(s.x, s.y), nmu2, u2_pair(acc[4 * i], acc[4 * i + 1])), ra2, f2_pack(b.x, b.y));
+      v[2 * i + 1] = f2_fma(f2_fma(f2_pack(s.z, s.w), nmu2, u2_pair(acc[4 * i + 2], acc[4 * i + 3])), ra2, f2_pack(b.z, b.w));
+    }
+  }
+}
+// Row statistics of the LayerNorm input from the producers' partial sums (nn.LayerNorm: biased variance, eps 1e-5).
+__device__ __forceinline__ void ln_row_coeffs(const GemmParams& p, const GemmGroup& g, int row, uint64_t& ra2, uint64_t& nmu2) {
+  float s = 0.f, q = 0.f;
+#ifdef SOME_DIAG_LNC_NOSTATS   // timing experiment only (wrong results)
+  if (false) {
+#else
+  if (row < p.M) {
+#endif
+    const float2* st = reinterpret_cast<const float2*>(g.ln_stats) + (size_t)row * SOME_LN_SLOTS;
+    for (int i = 0; i < p.ln_parts; ++i) {
+      const float2 t = st[i];
+      s += t.x, q += t.y;
+    }
+  }
+  const float inv_d = 1.0f / static_cast<float>(p.K);
+  const float mean = s * inv_d;
+  const float var = fmaxf(fmaf(-mean, mean, q * inv_d), 0.f);
+  const float ra = rsqrtf(var + 1e-5f);
+  ra2 = f2_pack(ra, ra);
+  nmu2 = f2_pack(-mean, -mean);
+}
 
 // One epilogue warp: rows [row_base, +32) x accumulator columns [col0, col0 + 128) of the tile (col_tile = first packed
 // column of the tile).  t_row = TMEM address of the warp's lane quadrant in the current accumulator stage.
-template <int EPI>
+// EPI = SOME_EPI_STORE_BF16 / SILU_BF16 / GLU_BF16; kLn = LayerNorm-folded consumer (SOME_EPI_LN_*).
+template <int EPI, bool kLn>
 __device__ __forceinline__ void epilogue_warp_staged(const GemmParams& p, const GemmGroup& g, int row_base, int lane,
                                                      uint32_t t_row, int col0, int col_tile, uint8_t* stage) {
   const int r = lane;  // row inside the warp's 32-row slab == TMEM lane offset
-  float4 rp[8];
+  uint64_t ra2 = 0, nmu2 = 0;
+  if constexpr (kLn) ln_row_coeffs(p, g, row_base + r, ra2, nmu2);
   if constexpr (EPI == SOME_EPI_STORE_BF16 || EPI == SOME_EPI_SILU_BF16) {
 #pragma unroll 1
     for (int sc = 0; sc < 2; ++sc) {  // 64 accumulator columns -> 64 bf16 = one 128-byte staged row
@@ -387,92 +439,41 @@ __device__ __forceinline__ void epilogue_warp_staged(const GemmParams& p, const 
         uint32_t acc[32];
         tmem_ld_32x32(t_row + c + hf * 32, acc);
         tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
-        add_bias32(g.bias, col_tile + c + hf * 32, v);
+        uint64_t v[16];
+        bias_or_ln32<kLn>(g, col_tile + c + hf * 32, acc, v, ra2, nmu2);
         if constexpr (EPI == SOME_EPI_SILU_BF16) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = silu_fast(v[i]);
+          for (int i = 0; i < 16; ++i) v[i] = silu_fast2(v[i]);
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           *reinterpret_cast<uint4*>(stage + stage_off(r, hf * 4 + q)) =
-              make_uint4(pack_bf16x2(v[8 * q + 0], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                         pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+              make_uint4(pack_bf16x2(v[4 * q]), pack_bf16x2(v[4 * q + 1]), pack_bf16x2(v[4 * q + 2]), pack_bf16x2(v[4 * q + 3]));
       }
       __syncwarp();
-      stage_flush<false>(p, g, row_base, lane, stage, (size_t)(col_tile + c) * 2, 2, rp);
+      stage_flush(p, g, row_base, lane, stage, (size_t)(col_tile + c) * 2);
       __syncwarp();
     }
-  } else if constexpr (EPI == SOME_EPI_GLU_BF16) {
+  } else {
+    static_assert(EPI == SOME_EPI_GLU_BF16, "staged epilogue: STORE / SILU / GLU only");
     // 128 packed columns (4 x [16 out | 16 gate]) -> 64 bf16 outputs = one staged row
 #pragma unroll
     for (int sub = 0; sub < 4; ++sub) {
       uint32_t acc[32];
       tmem_ld_32x32(t_row + col0 + sub * 32, acc);
       tmem_ld_wait();
-      float v[32];
+      uint64_t v[16];
+      bias_or_ln32<kLn>(g, col_tile + col0 + sub * 32, acc, v, ra2, nmu2);
+      uint32_t o[8];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
-      add_bias32(g.bias, col_tile + col0 + sub * 32, v);
-      float o[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) o[i] = v[i] * sigmoid_fast(v[16 + i]);
+      for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(f2_mul(v[i], sigmoid_fast2(v[8 + i])));
 #pragma unroll
       for (int q = 0; q < 2; ++q)
-        *reinterpret_cast<uint4*>(stage + stage_off(r, sub * 2 + q)) =
-            make_uint4(pack_bf16x2(o[8 * q + 0], o[8 * q + 1]), pack_bf16x2(o[8 * q + 2], o[8 * q + 3]),
-                       pack_bf16x2(o[8 * q + 4], o[8 * q + 5]), pack_bf16x2(o[8 * q + 6], o[8 * q + 7]));
+        *reinterpret_cast<uint4*>(stage + stage_off(r, sub * 2 + q)) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
     }
     __syncwarp();
-    stage_flush<false>(p, g, row_base, lane, stage, (size_t)((col_tile + col0) >> 1) * 2, 2, rp);
+    stage_flush(p, g, row_base, lane, stage, (size_t)((col_tile + col0) >> 1) * 2);
     __syncwarp();
-  } else if constexpr (EPI == SOME_EPI_RESID_F32) {
-#pragma unroll 1
-    for (int ch = 0; ch < 4; ++ch) {  // 32 accumulator columns -> 32 f32 = one staged row
-      const int c = col0 + ch * 32;
-      resid_prefetch(p, g, row_base, lane, (size_t)(col_tile + c) * 4, rp);  // coalesced, in flight during the math
-      uint32_t acc[32];
-      tmem_ld_32x32(t_row + c, acc);
-      tmem_ld_wait();
-      float v[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
-      add_bias32(g.bias, col_tile + c, v);
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        *reinterpret_cast<float4*>(stage + stage_off(r, q)) =
-            make_float4(p.alpha * v[4 * q], p.alpha * v[4 * q + 1], p.alpha * v[4 * q + 2], p.alpha * v[4 * q + 3]);
-      __syncwarp();
-      stage_flush<true>(p, g, row_base, lane, stage, (size_t)(col_tile + c) * 4, 4, rp);
-      __syncwarp();
-    }
-  } else if constexpr (EPI == SOME_EPI_GLU_RESID_F32) {
-#pragma unroll 1
-    for (int sc = 0; sc < 2; ++sc) {  // 64 packed columns -> 32 f32 outputs = one staged row
-      const int c = col0 + sc * 64;
-      const size_t out_byte = (size_t)((col_tile + c) >> 1) * 4;
-      resid_prefetch(p, g, row_base, lane, out_byte, rp);
-#pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {
-        uint32_t acc[32];
-        tmem_ld_32x32(t_row + c + sub * 32, acc);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
-        add_bias32(g.bias, col_tile + c + sub * 32, v);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<float4*>(stage + stage_off(r, sub * 4 + q)) =
-              make_float4(v[4 * q] * sigmoid_fast(v[16 + 4 * q]), v[4 * q + 1] * sigmoid_fast(v[16 + 4 * q + 1]),
-                          v[4 * q + 2] * sigmoid_fast(v[16 + 4 * q + 2]), v[4 * q + 3] * sigmoid_fast(v[16 + 4 * q + 3]));
-      }
-      __syncwarp();
-      stage_flush<true>(p, g, row_base, lane, stage, out_byte, 4, rp);
-      __syncwarp();
-    }
   }
 }
 
@@ -484,29 +485,48 @@ __device__ __forceinline__ void epilogue_warp_staged(const GemmParams& p, const 
 //   producer (warp 0, both CTAs): TMA with .cta_group::2, completion bytes land on the LEADER's full barrier
 //   MMA (warp 1, leader only): tcgen05.mma.cta_group::2 M256 N256 K16; commits are multicast to both CTAs
 //   epilogue (warps 4-11, both CTAs): own 128 TMEM lanes; tmem_empty arrivals go to the leader (remote arrive)
+//
+// Residual epilogues (RESID_F32, GLU_RESID_F32 and their LayerNorm-producer variants) move ALL of their global traffic
+// with TMA.  Per epilogue warp and 32-column chunk: the fp32 residual slab (32 rows x 128 B) is TMA-loaded one chunk ahead
+// into a 128-byte-swizzled shared-memory slab, so the thread that owns accumulator row r (tcgen05.ld: thread = row) reads
+// its row's residual conflict-free, adds alpha * (acc + bias) IN PLACE, and one elected lane TMA-stores the slab.  Nothing
+// goes through the LSU to global memory and no residual registers are held (the round-1 epilogue kept 32 and sat at ~0.69
+// of the HBM floor on the N = K = 512 GEMMs, profiles/r01_gemm_epilogue_lsu.txt).  Because the final row values pass
+// through the row-owning thread, the LayerNorm-producer variants get the row statistics for free: each thread sums x and
+// x^2 over its 128 (RESID) / 64 (GLU) columns of the tile, writes the pair into its slot of ln_stats, and also packs
+// bf16(x) into a third swizzled tile that is TMA-stored every second chunk (the consumer GEMM's A operand).
 constexpr int PAIR_BN = 256;
 constexpr int PAIR_STAGE_BYTES = BLOCK_M * BLOCK_K * 2 + (PAIR_BN / 2) * BLOCK_K * 2;  // 16 KB A + 16 KB half W
-// EXPERIMENT (off unless built with -DSOME_GEMM_BULK_RESID, tools/ab_bench.py; not validated on hardware yet): the residual
-// epilogue reads its residual slabs with cp.async.bulk into two extra 4 KB buffers per epilogue warp, one chunk ahead, instead of
-// through registers (the N = K = 512 residual GEMMs sit at ~54 % of the DRAM peak with one 4 KB slab in flight per warp and the
-// kernel at its register cap, profiles/r01_gemm_epilogue_lsu.txt).  It pays for the 64 KB with one pipeline stage.
-#ifdef SOME_GEMM_BULK_RESID
-constexpr bool kBulkResid = true;
-#else
-constexpr bool kBulkResid = false;
-#endif
+constexpr int PAIR_BAR_BYTES = 512;
+
+struct EpiMaps {        // tensor maps of the TMA epilogues, per group: residual (load), out (store), bf16 copy (store)
+  CUtensorMap r[2], o[2], xb[2];
+};
+
 template <int EPI>
 struct PairCfg {
-  static constexpr bool BULK = kBulkResid && EPI == SOME_EPI_RESID_F32;
-  static constexpr int STAGES = BULK ? 4 : 5;
-  static constexpr int EPI_BYTES = EPI_WARPS * (BULK ? 3 : 1) * 4096;  // per warp: 32 x 128 B transposition tile (+ 2 residual slabs)
-  static constexpr int SMEM = STAGES * PAIR_STAGE_BYTES + EPI_BYTES + 1024 + 256;
+  static constexpr bool LNP = EPI == SOME_EPI_RESID_F32_LN || EPI == SOME_EPI_GLU_RESID_F32_LN;
+  static constexpr bool GLU_R = EPI == SOME_EPI_GLU_RESID_F32 || EPI == SOME_EPI_GLU_RESID_F32_LN;
+  static constexpr bool TMA_EPI = LNP || EPI == SOME_EPI_RESID_F32 || EPI == SOME_EPI_GLU_RESID_F32;
+  static constexpr bool LNC = EPI == SOME_EPI_LN_STORE_BF16 || EPI == SOME_EPI_LN_SILU_BF16 || EPI == SOME_EPI_LN_GLU_BF16;
+  static constexpr int BASE = LNC ? EPI - SOME_EPI_LN_STORE_BF16 : EPI;   // staged epilogues: STORE / SILU / GLU
+#ifdef SOME_GEMM_LNP_STAGES
+  static constexpr int STAGES = LNP ? SOME_GEMM_LNP_STAGES : 5;
+#else
+  static constexpr int STAGES = LNP ? 4 : 5;
+#endif
+  // per epilogue warp: one 32 x 128 B transposition tile, or two residual slabs (+ the bf16 tile of the LN producers)
+  static constexpr int WARP_BYTES = TMA_EPI ? (LNP ? 12288 : 8192) : 4096;
+  static constexpr int EPI_BYTES = EPI_WARPS * WARP_BYTES;
+  static constexpr int SMEM = STAGES * PAIR_STAGE_BYTES + EPI_BYTES + 1024 + PAIR_BAR_BYTES;
+  static_assert(SMEM <= 232448, "gemm_pair_kernel: shared memory over the 227 KB per-CTA limit");
 };
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
-                 const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                 const __grid_constant__ EpiMaps em, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using Cfg = PairCfg<EPI>;
@@ -518,7 +538,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* tmem_full = bars + 2 * PAIR_STAGES;            // [2]       (local, multicast commit)
   uint64_t* tmem_empty = bars + 2 * PAIR_STAGES + 2;       // [2]       (used in the leader)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * PAIR_STAGES + 4);
-  [[maybe_unused]] uint64_t* resid_bar = bars + 2 * PAIR_STAGES + 6;   // [EPI_WARPS][2], bulk-residual experiment only
+  [[maybe_unused]] uint64_t* ld_bar = bars + 2 * PAIR_STAGES + 6;      // [EPI_WARPS][2] residual slabs (TMA epilogues)
+  static_assert(8 * (2 * PAIR_STAGES + 6 + 2 * EPI_WARPS) <= PAIR_BAR_BYTES, "barrier block too small");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -549,8 +570,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 2 * EPI_WARPS);
     }
-    if constexpr (Cfg::BULK) {
-      for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&resid_bar[i], 1);
+    if constexpr (Cfg::TMA_EPI) {
+      for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&ld_bar[i], 1);
     }
     fence_mbar_init();
   }
@@ -628,89 +649,165 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     constexpr int COLS_PER_WARP = PAIR_BN / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    // ---- bulk-residual experiment: chunk q of this warp (4 chunks of 32 columns per tile, q counts across tiles) lands in
-    //      residual slab q & 1; slab s is re-issued for chunk q + 2 as soon as chunk q has been flushed
-    [[maybe_unused]] uint8_t* rslab = epi_stage + EPI_WARPS * 4096 + ew * 8192;
-    [[maybe_unused]] uint64_t* rbar = resid_bar + 2 * ew;
-    [[maybe_unused]] auto issue_resid = [&](int tile_, int ch, int slab) {
-      if (tile_ >= num_tiles) return;
-      const int grp_ = tile_ / tiles_per_group;
-      const int t_ = tile_ - grp_ * tiles_per_group;
-      const int m_ = t_ / num_n, n_ = t_ - m_ * num_n;
-      const int row0 = m_ * 2 * BLOCK_M + rank * BLOCK_M + quad * 32;
-      const int rows = min(32, max(0, p.M - row0));
-      if (lane == 0) mbar_arrive_expect_tx(&rbar[slab], rows * 128);   // rows == 0: the plain arrival completes the phase
-      __syncwarp();
-      if (lane < rows) {
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.g[grp_].resid) +
-                             ((size_t)(row0 + lane) * p.ld_out + n_ * PAIR_BN + half * COLS_PER_WARP + ch * 32) * 4;
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 128, [%2];" ::"r"(
-                         smem_u32(rslab + slab * 4096 + lane * 128)),
-                     "l"(src), "r"(smem_u32(&rbar[slab]))
-                     : "memory");
-      }
-    };
-    [[maybe_unused]] int q = 0;
-    if constexpr (Cfg::BULK) {
-      issue_resid(pair, 0, 0);
-      issue_resid(pair, 1, 1);
-    }
-    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      const int grp = tile / tiles_per_group;
-      const int t = tile - grp * tiles_per_group;
-      const int m_blk = t / num_n, n_blk = t - m_blk * num_n;
-      const GemmGroup& g = p.g[grp];
-      const int row_base = m_blk * 2 * BLOCK_M + rank * BLOCK_M + quad * 32;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after_sync();
-      const uint32_t t_row = tmem_base + acc * PAIR_BN + (static_cast<uint32_t>(quad * 32) << 16);
-      if constexpr (Cfg::BULK) {
-        uint8_t* stage = epi_stage + ew * 4096;
+    if constexpr (Cfg::TMA_EPI) {
+      constexpr int NCH = Cfg::GLU_R ? 2 : 4;            // 32-output-column chunks per tile visit of this warp
+      uint8_t* wbase = epi_stage + ew * Cfg::WARP_BYTES;  // slab 0 | slab 1 | (bf16 tile)
+      uint64_t* lbar = ld_bar + 2 * ew;
+      // first output column / first row of chunk `ch` of tile `tile_` for this warp
+      auto coords = [&](int tile_, int ch, int& grp_, int& col_, int& row0_) {
+        grp_ = tile_ / tiles_per_group;
+        const int t_ = tile_ - grp_ * tiles_per_group;
+        const int m_ = t_ / num_n, n_ = t_ - m_ * num_n;
+        row0_ = m_ * 2 * BLOCK_M + rank * BLOCK_M + quad * 32;
+        col_ = Cfg::GLU_R ? n_ * (PAIR_BN / 2) + half * 64 + ch * 32 : n_ * PAIR_BN + half * COLS_PER_WARP + ch * 32;
+      };
+      auto issue_load = [&](int tile_, int ch, int slab) {   // lane 0 only: the bulk groups belong to the issuing thread
+        if (tile_ >= num_tiles) return;
+        int grp_, col_, row0_;
+        coords(tile_, ch, grp_, col_, row0_);
+        mbar_arrive_expect_tx(&lbar[slab], 4096);             // rows beyond M are zero-filled and still counted
+        tma_load_2d(wbase + slab * 4096, grp_ == 0 ? &em.r[0] : &em.r[1], &lbar[slab], col_, row0_);
+      };
+      uint32_t q = 0;   // chunk counter of this warp across tiles: chunk q lives in slab q & 1
+      if (lane == 0) issue_load(pair, 0, 0);
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        int grp, col_first, row_base;
+        coords(tile, 0, grp, col_first, row_base);
+        const int t = tile - grp * tiles_per_group;
+        const int n_blk = t - (t / num_n) * num_n;
+        const GemmGroup& g = p.g[grp];
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after_sync();
+        const uint32_t t_row = tmem_base + acc * PAIR_BN + (static_cast<uint32_t>(quad * 32) << 16) + half * COLS_PER_WARP;
+        // LayerNorm producers: sum x, sum x^2 of this thread's row over the warp's columns (two lanes each, added at the end)
+        [[maybe_unused]] uint64_t rs2 = f2_pack(0.f, 0.f), rq2 = rs2;
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch, ++q) {
+        for (int ch = 0; ch < NCH; ++ch, ++q) {
           const int slab = q & 1;
-          const int c = half * COLS_PER_WARP + ch * 32;
-          uint32_t accr[32];
-          tmem_ld_32x32(t_row + c, accr);
-          tmem_ld_wait();
-          float v[32];
+          // this chunk's 32 output columns of the thread's row, before the residual: 16 packed pairs
+          uint64_t v[16];
+          if constexpr (!Cfg::GLU_R) {
+            uint32_t a[32];
+            tmem_ld_32x32(t_row + ch * 32, a);
+            tmem_ld_wait();
+            bias_or_ln32<false>(g, n_blk * PAIR_BN + half * COLS_PER_WARP + ch * 32, a, v, 0, 0);
+          } else {
+            // 64 packed accumulator columns (2 x [16 out | 16 gate]) -> 32 outputs
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(accr[i]);
-          add_bias32(g.bias, n_blk * PAIR_BN + c, v);
+            for (int sub = 0; sub < 2; ++sub) {
+              uint32_t a[32];
+              tmem_ld_32x32(t_row + ch * 64 + sub * 32, a);
+              tmem_ld_wait();
+              uint64_t w[16];
+              bias_or_ln32<false>(g, n_blk * PAIR_BN + half * COLS_PER_WARP + ch * 64 + sub * 32, a, w, 0, 0);
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            *reinterpret_cast<float4*>(stage + stage_off(lane, k)) =
-                make_float4(p.alpha * v[4 * k], p.alpha * v[4 * k + 1], p.alpha * v[4 * k + 2], p.alpha * v[4 * k + 3]);
-          __syncwarp();
-          mbar_wait(&rbar[slab], (q >> 1) & 1);   // the residual slab of this chunk has landed
-          const uint8_t* rs = rslab + slab * 4096;
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int row = it * 4 + (lane >> 3), k = lane & 7;
-            if (row_base + row < p.M) {
-              const float4 a = *reinterpret_cast<const float4*>(stage + stage_off(row, k));
-              const float4 r4 = *reinterpret_cast<const float4*>(rs + row * 128 + k * 16);
-              *reinterpret_cast<float4*>(static_cast<uint8_t*>(g.out) +
-                                         ((size_t)(row_base + row) * p.ld_out + n_blk * PAIR_BN + c) * 4 + k * 16) =
-                  make_float4(a.x + r4.x, a.y + r4.y, a.z + r4.z, a.w + r4.w);
+              for (int i = 0; i < 8; ++i) v[sub * 8 + i] = f2_mul(w[i], sigmoid_fast2(w[8 + i]));
             }
           }
-          __syncwarp();   // every lane is done with the slab and the transposition tile
-          if (ch + 2 < 4) {
-            issue_resid(tile, ch + 2, slab);
-          } else {
-            issue_resid(tile + num_pairs, ch - 2, slab);
+          // the other slab (and the bf16 tile) were handed to TMA stores by the previous chunk: once those have read
+          // shared memory, prefetch the next chunk's residual into that slab
+          if (lane == 0) {
+            bulk_wait_group_read<0>();
+            if (ch + 1 < NCH) issue_load(tile, ch + 1, slab ^ 1);
+            else issue_load(tile + num_pairs, 0, slab ^ 1);
+          }
+          __syncwarp();
+          mbar_wait(&lbar[slab], (q >> 1) & 1);   // this chunk's residual has landed
+          uint8_t* sl = wbase + slab * 4096;
+          [[maybe_unused]] uint32_t pk[16];
+          const uint64_t alpha2 = f2_pack(p.alpha, p.alpha);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            ulonglong2* cell = reinterpret_cast<ulonglong2*>(sl + stage_off(lane, k));
+            ulonglong2 x = *cell;                     // residual: 4 consecutive columns as two packed pairs
+            if constexpr (Cfg::GLU_R) {
+              x.x = f2_add(x.x, v[2 * k]);
+              x.y = f2_add(x.y, v[2 * k + 1]);
+            } else {
+              x.x = f2_fma(v[2 * k], alpha2, x.x);    // alpha * (acc + bias) + resid
+              x.y = f2_fma(v[2 * k + 1], alpha2, x.y);
+            }
+            *cell = x;
+            if constexpr (Cfg::LNP) {
+#ifndef SOME_DIAG_LNP_NOSTATS  // timing experiment only (wrong results)
+              rs2 = f2_add(rs2, f2_add(x.x, x.y));
+              rq2 = f2_fma(x.x, x.x, f2_fma(x.y, x.y, rq2));
+#endif
+#ifndef SOME_DIAG_LNP_NOXB
+              pk[2 * k] = pack_bf16x2(x.x);
+              pk[2 * k + 1] = pack_bf16x2(x.y);
+#endif
+            }
+          }
+#ifndef SOME_DIAG_LNP_NOXB
+          if constexpr (Cfg::LNP) {
+            uint8_t* xt = wbase + 8192;   // 32 rows x 64 bf16: chunk ch fills the 16-byte cells 4 (ch & 1) .. + 3 of each row
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(xt + stage_off(lane, (ch & 1) * 4 + j)) =
+                  make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+#endif
+          fence_proxy_async_smem();   // generic-proxy writes above -> visible to the TMA (async proxy) reads below
+          __syncwarp();
+          if (lane == 0) {
+            const int col = col_first + ch * 32;
+            tma_store_2d(grp == 0 ? &em.o[0] : &em.o[1], sl, col, row_base);
+#ifndef SOME_DIAG_LNP_NOXB
+            if constexpr (Cfg::LNP) {
+              if (ch & 1) tma_store_2d(grp == 0 ? &em.xb[0] : &em.xb[1], wbase + 8192, col - 32, row_base);
+            }
+#endif
+            bulk_commit_group();
           }
         }
-      } else {
-      epilogue_warp_staged<EPI>(p, g, row_base, lane, t_row, half * COLS_PER_WARP, n_blk * PAIR_BN, epi_stage + ew * 4096);
+        if constexpr (Cfg::LNP) {
+          float s0, s1, q0, q1;
+          f2_unpack(rs2, s0, s1);
+          f2_unpack(rq2, q0, q1);
+          if (row_base + lane < p.M)
+            reinterpret_cast<float2*>(g.ln_stats)[(size_t)(row_base + lane) * SOME_LN_SLOTS + n_blk * 2 + half] =
+                make_float2(s0 + s1, q0 + q1);
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
       }
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
+      if (lane == 0) bulk_wait_group_read<0>();   // shared memory must outlive the last TMA stores' reads
+    } else {
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int grp = tile / tiles_per_group;
+        const int t = tile - grp * tiles_per_group;
+        const int m_blk = t / num_n, n_blk = t - m_blk * num_n;
+        const GemmGroup& g = p.g[grp];
+        const int row_base = m_blk * 2 * BLOCK_M + rank * BLOCK_M + quad * 32;
+        if constexpr (Cfg::LNC) {
+          // The row statistics of the NEXT tile are pulled into L1 now: read at the start of that tile's epilogue they would
+          // cost a DRAM round trip with nothing to overlap it (measured: +25 % on the K = 512 consumer GEMMs).
+          const int nt = tile + num_pairs;
+          if (nt < num_tiles) {
+            const int ng = nt / tiles_per_group;
+            const int nrow = ((nt - ng * tiles_per_group) / num_n) * 2 * BLOCK_M + rank * BLOCK_M + quad * 32 + lane;
+            if (nrow < p.M)
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(p.g[ng].ln_stats + (size_t)nrow * SOME_LN_SLOTS * 2));
+          }
+        }
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after_sync();
+        const uint32_t t_row = tmem_base + acc * PAIR_BN + (static_cast<uint32_t>(quad * 32) << 16);
+        epilogue_warp_staged<Cfg::BASE, Cfg::LNC>(p, g, row_base, lane, t_row, half * COLS_PER_WARP, n_blk * PAIR_BN,
+                                                  epi_stage + ew * 4096);
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
       }
     }
   }
@@ -724,19 +821,20 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 }
 
 template <int EPI>
-static int launch_gemm_pair(const CUtensorMap* maps, const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm_pair(const CUtensorMap* maps, const EpiMaps& em, const GemmParams& p, cudaStream_t stream) {
   auto kern = gemm_pair_kernel<EPI>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};   // function attributes are per device
+  const int dev_ = device_index();
+  if (!configured[dev_]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<EPI>::SMEM);
     SOME_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(gemm_pair, %d B smem): %s", PairCfg<EPI>::SMEM, cudaGetErrorString(e));
-    configured = true;
+    configured[dev_] = true;
   }
   const int num_m = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   const int tiles = num_m * (p.N / PAIR_BN) * p.groups;
   int pairs = num_sms() / 2;
   if (tiles < pairs) pairs = tiles;
-  kern<<<2 * pairs, GEMM_THREADS, PairCfg<EPI>::SMEM, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+  kern<<<2 * pairs, GEMM_THREADS, PairCfg<EPI>::SMEM, stream>>>(maps[0], maps[1], maps[2], maps[3], em, p);
   return check_launch("some_gemm(pair)");
 }
 
@@ -744,11 +842,12 @@ template <int BLOCK_N, int EPI>
 static int launch_gemm(const CUtensorMap* maps, const GemmParams& p, cudaStream_t stream) {
   using S = GemmSmem<BLOCK_N>;
   auto kern = gemm_kernel<BLOCK_N, EPI>;
-  static bool configured = false;  // benign race: idempotent attribute set
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};   // function attributes are per device
+  const int dev_ = device_index();
+  if (!configured[dev_]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     SOME_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(gemm, %d B smem): %s", S::TOTAL, cudaGetErrorString(e));
-    configured = true;
+    configured[dev_] = true;
   }
   const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
@@ -773,6 +872,10 @@ extern "C" int some_gemm(const some_gemm_args* a, cudaStream_t stream) {
   const bool head = (epi == SOME_EPI_SOFTMAX_F32 || epi == SOME_EPI_SIGMOID_F32 || epi == SOME_EPI_BIAS_F32);
   if (!head) SOME_REQUIRE(a->N % 256 == 0, "some_gemm: N must be a multiple of 256 for epilogue %d (got %d)", epi, a->N);
   if (epi == SOME_EPI_SOFTMAX_F32) SOME_REQUIRE(a->N <= 256, "some_gemm: softmax epilogue needs N <= 256");
+  const bool ln_consumer = epi == SOME_EPI_LN_STORE_BF16 || epi == SOME_EPI_LN_SILU_BF16 || epi == SOME_EPI_LN_GLU_BF16;
+  const bool ln_producer = epi == SOME_EPI_RESID_F32_LN || epi == SOME_EPI_GLU_RESID_F32_LN;
+  const bool glu_resid = epi == SOME_EPI_GLU_RESID_F32 || epi == SOME_EPI_GLU_RESID_F32_LN;
+  const bool needs_resid = epi == SOME_EPI_RESID_F32 || epi == SOME_EPI_RESID_F32_LN || glu_resid;
   GemmParams p;
   p.M = a->M;
   p.N = a->N;
@@ -781,8 +884,16 @@ extern "C" int some_gemm(const some_gemm_args* a, cudaStream_t stream) {
   p.ld_out = a->ld_out;
   p.n_valid = a->N;
   p.alpha = a->alpha;
+  p.ln_parts = a->ln_parts;
+  if (ln_consumer)
+    SOME_REQUIRE(a->ln_parts >= 1 && a->ln_parts <= SOME_LN_SLOTS, "some_gemm: ln_parts must be in [1, %d] (got %d)",
+                 SOME_LN_SLOTS, a->ln_parts);
+  if (ln_producer)
+    SOME_REQUIRE((glu_resid ? a->N / 2 : a->N) / 128 <= SOME_LN_SLOTS, "some_gemm: LayerNorm producer output too wide (N=%d)", a->N);
   const bool use_pair = !head;   // 256 x 256 CTA-pair tiles for every trunk GEMM; heads / input projection stay 1-CTA
   CUtensorMap maps[4];
+  EpiMaps em;
+  memset(&em, 0, sizeof(em));
   for (int g = 0; g < 2; ++g) {
     const int s = g < a->groups ? g : 0;
     SOME_REQUIRE(a->A[s] != nullptr && a->W[s] != nullptr && a->out[s] != nullptr, "some_gemm: null pointer in group %d", s);
@@ -791,15 +902,35 @@ extern "C" int some_gemm(const some_gemm_args* a, cudaStream_t stream) {
     p.g[g].bias = a->bias[s];
     p.g[g].out = a->out[s];
     p.g[g].resid = a->resid[s];
+    p.g[g].ln_s = a->ln_s[s];
+    p.g[g].ln_stats = a->ln_stats[s];
+    if (needs_resid) {
+      const int out_cols = glu_resid ? a->N / 2 : a->N;
+      SOME_REQUIRE(a->resid[s] != nullptr, "some_gemm: epilogue %d needs a residual pointer (group %d)", epi, s);
+      SOME_REQUIRE(a->ld_out % 4 == 0 && out_cols <= a->ld_out, "some_gemm: bad ld_out %d for %d output columns", a->ld_out, out_cols);
+      if (make_tmap_2d(&em.r[g], 4, a->resid[s], a->M, out_cols, a->ld_out, 32, 32)) return -1;
+      if (make_tmap_2d(&em.o[g], 4, a->out[s], a->M, out_cols, a->ld_out, 32, 32)) return -1;
+      if (ln_producer) {
+        SOME_REQUIRE(a->out_bf16[s] != nullptr && a->ln_stats[s] != nullptr,
+                     "some_gemm: LayerNorm producer epilogue %d needs out_bf16 and ln_stats (group %d)", epi, s);
+        if (make_tmap_2d(&em.xb[g], 2, a->out_bf16[s], a->M, out_cols, a->ld_out, 32, 64)) return -1;
+      }
+    }
+    if (ln_consumer)
+      SOME_REQUIRE(a->ln_s[s] != nullptr && a->ln_stats[s] != nullptr && a->bias[s] != nullptr,
+                   "some_gemm: LayerNorm consumer epilogue %d needs bias, ln_s and ln_stats (group %d)", epi, s);
   }
-  const bool needs_resid = (epi == SOME_EPI_RESID_F32 || epi == SOME_EPI_GLU_RESID_F32);
-  if (needs_resid) SOME_REQUIRE(a->resid[0] != nullptr, "some_gemm: epilogue %d needs a residual pointer", epi);
   switch (epi) {
-    case SOME_EPI_STORE_BF16: return launch_gemm_pair<SOME_EPI_STORE_BF16>(maps, p, stream);
-    case SOME_EPI_SILU_BF16: return launch_gemm_pair<SOME_EPI_SILU_BF16>(maps, p, stream);
-    case SOME_EPI_GLU_BF16: return launch_gemm_pair<SOME_EPI_GLU_BF16>(maps, p, stream);
-    case SOME_EPI_RESID_F32: return launch_gemm_pair<SOME_EPI_RESID_F32>(maps, p, stream);
-    case SOME_EPI_GLU_RESID_F32: return launch_gemm_pair<SOME_EPI_GLU_RESID_F32>(maps, p, stream);
+    case SOME_EPI_STORE_BF16: return launch_gemm_pair<SOME_EPI_STORE_BF16>(maps, em, p, stream);
+    case SOME_EPI_SILU_BF16: return launch_gemm_pair<SOME_EPI_SILU_BF16>(maps, em, p, stream);
+    case SOME_EPI_GLU_BF16: return launch_gemm_pair<SOME_EPI_GLU_BF16>(maps, em, p, stream);
+    case SOME_EPI_RESID_F32: return launch_gemm_pair<SOME_EPI_RESID_F32>(maps, em, p, stream);
+    case SOME_EPI_GLU_RESID_F32: return launch_gemm_pair<SOME_EPI_GLU_RESID_F32>(maps, em, p, stream);
+    case SOME_EPI_LN_STORE_BF16: return launch_gemm_pair<SOME_EPI_LN_STORE_BF16>(maps, em, p, stream);
+    case SOME_EPI_LN_SILU_BF16: return launch_gemm_pair<SOME_EPI_LN_SILU_BF16>(maps, em, p, stream);
+    case SOME_EPI_LN_GLU_BF16: return launch_gemm_pair<SOME_EPI_LN_GLU_BF16>(maps, em, p, stream);
+    case SOME_EPI_RESID_F32_LN: return launch_gemm_pair<SOME_EPI_RESID_F32_LN>(maps, em, p, stream);
+    case SOME_EPI_GLU_RESID_F32_LN: return launch_gemm_pair<SOME_EPI_GLU_RESID_F32_LN>(maps, em, p, stream);
     case SOME_EPI_BIAS_F32: return launch_gemm<256, SOME_EPI_BIAS_F32>(maps, p, stream);
     case SOME_EPI_SIGMOID_F32: return launch_gemm<256, SOME_EPI_SIGMOID_F32>(maps, p, stream);
     case SOME_EPI_SOFTMAX_F32: return launch_gemm<256, SOME_EPI_SOFTMAX_F32>(maps, p, stream);

@@ -18,6 +18,14 @@ int check_launch(const char* what);
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                       uint32_t box_rows, uint32_t box_cols = 64);
 
+// same for any element size (2 = bf16, 4 = f32): the inner box extent is always 128 bytes (64 bf16 / 32 f32 columns)
+int make_tmap_2d(CUtensorMap* out, uint32_t elem_bytes, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                 uint32_t box_rows, uint32_t box_cols);
+
+// Function attributes (dynamic shared-memory opt-in, carveout) and the SM count are per DEVICE: everything that caches them
+// indexes by the current device so that engines on several GPUs of one process work (one slot per device ordinal).
+constexpr int kMaxDevices = 64;
+int device_index();
 int num_sms();
 
 #define SOME_REQUIRE(cond, ...)      \

@@ -3,15 +3,17 @@
 // `.transpose(1, 2)` (inference/me_infer.py:31) disappears.  Restates modules/rmvpe/spec.py:38-72
 // (keyshift = 0, speed = 1, center = True).
 //
-// CTA = 16 consecutive frames of one clip (256 threads, two frames in flight, 128 threads each).
-//   1. the (16 + 3) x 512 samples the frames overlap are staged once in shared memory with coalesced
-//      float4 loads; samples outside [0, L) read as zero (the reference's F.pad 1024 / 1024);
-//   2. per frame: z[n] = w[2n] x[2n] + i w[2n+1] x[2n+1], in-place radix-4 DIF FFT of 1024 complex points in
-//      shared memory (5 stages, host-computed double-precision per-stage twiddle tables), result in base-4 digit-reversed order;
-//   3. real-FFT unpack for bins 0..371 only (mel weights above 8 kHz are zero), |X|;
-//   4. mel[m] = sum over the filter's contiguous bin range (<= 24 bins), log(max(., clamp)).
-// Algorithmic traffic: 512 x 4 B in + 80 x 4 B out per frame (2368 B); the FFT itself (~56 kFLOP/frame fp32,
-// 80 KB of shared-memory traffic) makes this kernel shared-memory/FMA bound rather than HBM bound.
+// ONE WARP PER FRAME, the FFT in registers (round 1 ran five radix-4 stages through shared memory with a CTA barrier after
+// each: 1.45 ms per 64 x 30 s batch, 4 % of the HBM rate).  The 2048 real samples are packed as 1024 complex points
+// z[n] = w[2n] x[2n] + i w[2n+1] x[2n+1] and transformed as 32 x 32 (Cooley-Tukey, n = 32 n1 + n2, k = k1 + 32 k2):
+//   1. lane n2 loads z[32 n1 + n2], n1 < 32 (coalesced 8-byte loads straight from the waveform; samples outside [0, L) read
+//      as zero = the reference's F.pad 1024 / 1024) and runs a 32-point radix-2 DIF DFT over n1 in registers;
+//   2. times W_1024^(n2 k1) (table [k1][n2], conflict-free), transposed through a warp-private 8 KB XOR-swizzled tile;
+//   3. lane k1 runs the second 32-point DFT over n2 -> Z[k1 + 32 k2], written back to the tile in natural order;
+//   4. real-FFT unpack for bins 0..371 only (mel weights above 8 kHz are zero), |X| -> the tile (as floats);
+//   5. mel[m] = sum over the filter's contiguous bin range (<= 24 bins), log(max(., clamp)); lane m, m + 32, m + 64.
+// No CTA barrier after the table load; a CTA is just MEL_WARPS independent warps sharing the 19 KB of tables.
+// Algorithmic traffic: 512 x 4 B in + 80 x 4 B out per frame (2368 B); ~60 kFLOP per frame keep it issue-bound.
 #include "host_common.h"
 #include "sm100_ptx.cuh"
 
@@ -19,40 +21,70 @@
 
 namespace some {
 
-constexpr int MEL_FPB = 16;                    // frames per CTA
-constexpr int MEL_NS = (MEL_FPB + 3) * 512;    // staged samples
+constexpr int MEL_WARPS = 4;                   // warps per CTA
+constexpr int MEL_FPW = 8;                     // consecutive frames per warp (75 % of a frame's samples are L1 hits)
+constexpr int MEL_FPB = MEL_WARPS * MEL_FPW;   // frames per CTA
 constexpr int MEL_MAXW = SOME_MEL_MAXW;
-constexpr int MEL_TW = SOME_MEL_TW;             // per-stage twiddles (3 x 256 | 3 x 64 | 3 x 16 | 3 x 4) + 372 unpack
-constexpr int MEL_SMEM = MEL_NS * 4 + MEL_TW * 8 /*twiddle*/ + 2048 * 4 /*window*/ + 2 * 1024 * 8 /*work*/ +
-                         2 * SOME_MEL_BINS * 4 /*mag*/;
+constexpr int MEL_TW = SOME_MEL_TW;            // 1024 inter-pass twiddles [k1][n2] + 372 unpack twiddles
+constexpr int MEL_SMEM = MEL_TW * 8 + 2048 * 4 /*window*/ + MEL_WARPS * 1024 * 8 /*tiles*/;
 
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+struct cpx {
+  float x, y;
+};
+__device__ __forceinline__ cpx cadd(cpx a, cpx b) { return {a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ cpx csub(cpx a, cpx b) { return {a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ cpx cmul(cpx a, float wr, float wi) { return {a.x * wr - a.y * wi, a.x * wi + a.y * wr}; }
+
+// W_32^j = exp(-2 pi i j / 32), j < 16 (rounded from double)
+__device__ constexpr float kC32[16] = {1.0f,          0.98078528f,  0.92387953f,  0.83146961f, 0.70710678f,  0.55557023f,
+                                       0.38268343f,   0.19509032f,  0.0f,         -0.19509032f, -0.38268343f, -0.55557023f,
+                                       -0.70710678f,  -0.83146961f, -0.92387953f, -0.98078528f};
+__device__ constexpr float kS32[16] = {0.0f,          -0.19509032f, -0.38268343f, -0.55557023f, -0.70710678f, -0.83146961f,
+                                       -0.92387953f,  -0.98078528f, -1.0f,        -0.98078528f, -0.92387953f, -0.83146961f,
+                                       -0.70710678f,  -0.55557023f, -0.38268343f, -0.19509032f};
+
+// In-place 32-point radix-2 DIF DFT, fully unrolled (all indices and twiddles are compile-time): c[i] ends up holding
+// X[bitrev5(i)].
+__device__ __forceinline__ void dft32(cpx (&c)[32]) {
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const int half = 16 >> s;
+#pragma unroll
+    for (int g = 0; g < 32; g += 2 * half) {
+#pragma unroll
+      for (int j = 0; j < half; ++j) {
+        const cpx a = c[g + j], b = c[g + j + half];
+        c[g + j] = cadd(a, b);
+        const cpx d = csub(a, b);
+        const int t = j * (16 / half);   // W_(2 half)^j = W_32^t
+        if (t == 0) {
+          c[g + j + half] = d;
+        } else if (t == 8) {             // -i
+          c[g + j + half] = {d.y, -d.x};
+        } else {
+          c[g + j + half] = cmul(d, kC32[t], kS32[t]);
+        }
+      }
+    }
+  }
 }
-// position of X[k] after the in-place radix-4 DIF: reverse the five base-4 digits of k
-__device__ __forceinline__ int rev4_10(int k) {
-  const int b = __brev(static_cast<unsigned>(k)) >> 22;  // 10-bit reversal
-  return ((b & 0x2AA) >> 1) | ((b & 0x155) << 1);        // swap the bits inside each digit back
+__device__ __forceinline__ constexpr int bitrev5(int i) {
+  return ((i & 1) << 4) | ((i & 2) << 2) | (i & 4) | ((i & 8) >> 2) | ((i & 16) >> 4);
 }
+// warp-private 32 x 32 complex tile, element (row, col) with the column XOR-swizzled by the row: a lane writing its 32
+// values down a column and a lane reading its 32 values along a row are both conflict-free (8-byte accesses, half-warps)
+__device__ __forceinline__ int tsw(int row, int col) { return row * 32 + (col ^ row); }
 
-// Shared-memory index swizzle of the 1024-point work buffer (float2 elements, 16 per 128-byte bank row): the low four
-// index bits are XORed with bits 4-5 (twice) and bits 6-9, which keeps every access pattern of the kernel conflict-free:
-// the strided butterflies of the last two radix-4 stages (threads differ in bits 2-5) and the digit-reversed reads of
-// the real-FFT unpack (consecutive bins differ only in bits 6-9).
-__device__ __forceinline__ int zsw(int i) { return i ^ (((i >> 4) & 3) * 5) ^ ((i >> 6) & 15); }
-
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(MEL_WARPS * 32, 4)
 mel_kernel(const float* __restrict__ wave, const int64_t* __restrict__ clip_start, const int64_t* __restrict__ clip_len,
            const int32_t* __restrict__ cu_frames,
            int tiles_per_clip, const int32_t* __restrict__ mel_start, const int32_t* __restrict__ mel_count,
            const float* __restrict__ mel_weights, const float* __restrict__ twiddle, const float* __restrict__ window,
            float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, float clamp) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  float* s_x = reinterpret_cast<float*>(smem_raw);
-  float2* s_tw = reinterpret_cast<float2*>(s_x + MEL_NS);
+  float2* s_tw = reinterpret_cast<float2*>(smem_raw);             // [1024] W_1024^(n2 k1) at [k1 * 32 + n2], then [372] W_2048^k
   float* s_win = reinterpret_cast<float*>(s_tw + MEL_TW);
-  float2* s_work = reinterpret_cast<float2*>(s_win + 2048);
-  float* s_mag = reinterpret_cast<float*>(s_work + 2 * 1024);
+  float2* s_tiles = reinterpret_cast<float2*>(s_win + 2048);
 
   const int clip = blockIdx.x / tiles_per_clip;
   const int tile = blockIdx.x - clip * tiles_per_clip;
@@ -60,111 +92,105 @@ mel_kernel(const float* __restrict__ wave, const int64_t* __restrict__ clip_star
   const int T = cu_frames[clip + 1] - row_begin;
   const int frame0 = tile * MEL_FPB;
   if (frame0 >= T) return;
-  const int64_t off = clip_start[clip];
   const int64_t L = clip_len[clip];
-  const float* __restrict__ x = wave + off;
-  const int nframes = min(MEL_FPB, T - frame0);
+  const float* __restrict__ x = wave + clip_start[clip];
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
 
-  // ---- stage samples [frame0 * 512 - 1024, +MEL_NS) of the clip; zero outside [0, L)
-  const int64_t s0 = static_cast<int64_t>(frame0) * 512 - 1024;
-  const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  for (int i = threadIdx.x * 4; i < MEL_NS; i += 256 * 4) {
-    const int64_t s = s0 + i;
-    float4 v;
-    if (vec_ok && s >= 0 && s + 3 < L) {
-      v = *reinterpret_cast<const float4*>(x + s);
-    } else {
-      v.x = (s >= 0 && s < L) ? x[s] : 0.f;
-      v.y = (s + 1 >= 0 && s + 1 < L) ? x[s + 1] : 0.f;
-      v.z = (s + 2 >= 0 && s + 2 < L) ? x[s + 2] : 0.f;
-      v.w = (s + 3 >= 0 && s + 3 < L) ? x[s + 3] : 0.f;
-    }
-    *reinterpret_cast<float4*>(s_x + i) = v;
-  }
-  for (int i = threadIdx.x; i < MEL_TW; i += 256) s_tw[i] = reinterpret_cast<const float2*>(twiddle)[i];
-  for (int i = threadIdx.x; i < 2048; i += 256) s_win[i] = window[i];
+  for (int i = threadIdx.x; i < MEL_TW; i += MEL_WARPS * 32) s_tw[i] = reinterpret_cast<const float2*>(twiddle)[i];
+  for (int i = threadIdx.x; i < 2048; i += MEL_WARPS * 32) s_win[i] = window[i];
   __syncthreads();
 
-  const int slot = threadIdx.x >> 7;   // which of the two in-flight frames
-  const int tid = threadIdx.x & 127;
-  float2* z = s_work + slot * 1024;
-  float* mag = s_mag + slot * SOME_MEL_BINS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2* tile_z = s_tiles + warp * 1024;
+  float* mag = reinterpret_cast<float*>(tile_z);
+  // mel filters of this lane: m = lane, lane + 32, lane + 64 (< 80)
+  int m_st[3], m_cn[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int m = lane + 32 * i;
+    m_st[i] = m < SOME_N_MELS ? __ldg(mel_start + m) : 0;
+    m_cn[i] = m < SOME_N_MELS ? __ldg(mel_count + m) : 0;
+  }
 
-  for (int fpair = 0; fpair < MEL_FPB; fpair += 2) {
-    const int f = fpair + slot;          // frame within the CTA
-    const bool active = f < nframes;     // uniform per 128-thread half
-    // ---- window + pack: z[n] = (w[2n] x[2n], w[2n+1] x[2n+1])
-    if (active) {
-      const float* xf = s_x + f * 512;
-      for (int n = tid; n < 1024; n += 128) {
-        const float2 xv = *reinterpret_cast<const float2*>(xf + 2 * n);
-        const float2 wv = *reinterpret_cast<const float2*>(s_win + 2 * n);
-        z[zsw(n)] = make_float2(xv.x * wv.x, xv.y * wv.y);
-      }
-    }
-    __syncthreads();
-    // ---- 5 radix-4 DIF stages, in place
+  for (int fi = 0; fi < MEL_FPW; ++fi) {
+    const int f = frame0 + warp * MEL_FPW + fi;
+    if (f >= T) break;   // warp-uniform
+    // ---- 1. load + window + first DFT (over n1, lane = n2)
+    cpx c[32];
+    const int64_t s0 = static_cast<int64_t>(f) * 512 - 1024 + 2 * lane;   // sample index of z[n2]'s real part for n1 = 0
 #pragma unroll
-    for (int s = 0; s < 5; ++s) {
-      const int Lg = 1024 >> (2 * s);  // current group length
-      const int q = Lg >> 2;
-      if (active) {
+    for (int n1 = 0; n1 < 32; ++n1) {
+      const int64_t s = s0 + 64 * n1;
+      float2 xv;
+      if (vec_ok && s >= 0 && s + 1 < L) {
+        xv = __ldg(reinterpret_cast<const float2*>(x + s));
+      } else {
+        xv.x = (s >= 0 && s < L) ? __ldg(x + s) : 0.f;
+        xv.y = (s + 1 >= 0 && s + 1 < L) ? __ldg(x + s + 1) : 0.f;
+      }
+      const float2 wv = *reinterpret_cast<const float2*>(s_win + 64 * n1 + 2 * lane);
+      c[n1] = {xv.x * wv.x, xv.y * wv.y};
+    }
+    dft32(c);
+    // ---- 2. twiddle W_1024^(n2 k1) and transpose: register i holds k1 = bitrev5(i)
+    __syncwarp();   // the previous frame's mel pass has finished reading the tile
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int b = tid + 128 * i;
-          const int grp = b / q, j = b - grp * q;
-          const int base = grp * Lg + j;
-          const int i0 = zsw(base), i1 = zsw(base + q), i2 = zsw(base + 2 * q), i3 = zsw(base + 3 * q);
-          const float2 a = z[i0], bb = z[i1], c = z[i2], d = z[i3];
-          const float2 t0 = make_float2(a.x + c.x, a.y + c.y);
-          const float2 t1 = make_float2(a.x - c.x, a.y - c.y);
-          const float2 t2 = make_float2(bb.x + d.x, bb.y + d.y);
-          const float2 t3 = make_float2(bb.y - d.y, -(bb.x - d.x));  // -i (b - d)
-          float2 y0 = make_float2(t0.x + t2.x, t0.y + t2.y);
-          float2 y1 = make_float2(t1.x + t3.x, t1.y + t3.y);
-          float2 y2 = make_float2(t0.x - t2.x, t0.y - t2.y);
-          float2 y3 = make_float2(t1.x - t3.x, t1.y - t3.y);
-          if (s < 4) {  // last stage: all twiddles are 1
-            // per-stage tables W_Lg^(m j), m = 1..3, j < q, contiguous in j: consecutive threads -> consecutive words
-            // (a single strided W_2048 table made these reads up to 16-way bank conflicted)
-            constexpr int kOff[4] = {0, 768, 960, 1008};
-            const float2* tws = s_tw + kOff[s];
-            y1 = cmul(y1, tws[j]);
-            y2 = cmul(y2, tws[q + j]);
-            y3 = cmul(y3, tws[2 * q + j]);
-          }
-          z[i0] = y0, z[i1] = y1, z[i2] = y2, z[i3] = y3;
-        }
-      }
-      __syncthreads();
+    for (int i = 0; i < 32; ++i) {
+      const int k1 = bitrev5(i);
+      const float2 w = s_tw[k1 * 32 + lane];
+      const cpx v = cmul(c[i], w.x, w.y);
+      tile_z[tsw(k1, lane)] = make_float2(v.x, v.y);
     }
-    // ---- real-FFT unpack, bins 0..371:  X[k] = E + W_2048^k O,  E = (Z[k] + conj Z[N-k]) / 2,
-    //      O = -i (Z[k] - conj Z[N-k]) / 2
-    if (active) {
-      for (int k = tid; k < SOME_MEL_BINS; k += 128) {
-        const float2 zk = z[zsw(rev4_10(k))];
-        const float2 zn = z[zsw(rev4_10((1024 - k) & 1023))];
-        const float2 E = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-        const float2 dlt = make_float2(zk.x - zn.x, zk.y + zn.y);  // Z[k] - conj(Z[N-k])
-        const float2 O = make_float2(0.5f * dlt.y, -0.5f * dlt.x);  // -i/2 * dlt
-        const float2 wo = cmul(s_tw[1020 + k], O);  // W_2048^k
-        const float re = E.x + wo.x, im = E.y + wo.y;
-        mag[k] = sqrtf(re * re + im * im);
+    __syncwarp();
+    // ---- 3. second DFT (over n2, lane = k1)
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) {
+      const float2 v = tile_z[tsw(lane, n2)];
+      c[n2] = {v.x, v.y};
+    }
+    dft32(c);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) tile_z[lane + 32 * bitrev5(i)] = make_float2(c[i].x, c[i].y);   // Z[k1 + 32 k2], natural order
+    __syncwarp();
+    // ---- 4. real-FFT unpack, bins 0..371:  X[k] = E + W_2048^k O,  E = (Z[k] + conj Z[N-k]) / 2,
+    //         O = -i (Z[k] - conj Z[N-k]) / 2;  all reads first, then the magnitudes overwrite the tile
+    float mg[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      const int k = lane + 32 * i;
+      mg[i] = 0.f;
+      if (k < SOME_MEL_BINS) {
+        const float2 zk = tile_z[k];
+        const float2 zn = tile_z[(1024 - k) & 1023];
+        const float ex = 0.5f * (zk.x + zn.x), ey = 0.5f * (zk.y - zn.y);
+        const float dx = zk.x - zn.x, dy = zk.y + zn.y;   // Z[k] - conj(Z[N-k])
+        const float ox = 0.5f * dy, oy = -0.5f * dx;      // -i/2 * that
+        const float2 w = s_tw[1024 + k];                  // W_2048^k
+        const float re = ex + (w.x * ox - w.y * oy), im = ey + (w.x * oy + w.y * ox);
+        mg[i] = sqrtf(re * re + im * im);
       }
     }
-    __syncthreads();
-    // ---- mel + log
-    if (active && tid < SOME_N_MELS) {
-      const int st = __ldg(mel_start + tid), cn = __ldg(mel_count + tid);
-      float acc = 0.f;
-      for (int i = 0; i < cn; ++i) acc = fmaf(__ldg(mel_weights + tid * MEL_MAXW + i), mag[st + i], acc);
-      const float v = logf(fmaxf(acc, clamp));
-      const size_t o = static_cast<size_t>(row_begin + frame0 + f) * SOME_N_MELS + tid;
-      if (out_f32 != nullptr) out_f32[o] = v;
-      if (out_bf16 != nullptr) out_bf16[o] = __float2bfloat16_rn(v);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      const int k = lane + 32 * i;
+      if (k < SOME_MEL_BINS) mag[k] = mg[i];
     }
-    // the next iteration's pack overwrites z only after the unpack above (barrier), and mag only after the
-    // stage barriers of the next FFT, so no extra barrier is needed here.
+    __syncwarp();
+    // ---- 5. mel + log
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int m = lane + 32 * i;
+      if (m < SOME_N_MELS) {
+        float acc = 0.f;
+        for (int j = 0; j < m_cn[i]; ++j) acc = fmaf(__ldg(mel_weights + m * MEL_MAXW + j), mag[m_st[i] + j], acc);
+        const float v = logf(fmaxf(acc, clamp));
+        const size_t o = static_cast<size_t>(row_begin + f) * SOME_N_MELS + m;
+        if (out_f32 != nullptr) out_f32[o] = v;
+        if (out_bf16 != nullptr) out_bf16[o] = __float2bfloat16_rn(v);
+      }
+    }
   }
 }
 
@@ -181,16 +207,17 @@ extern "C" int some_mel_logmel(const float* wave, const int64_t* clip_start, con
                "some_mel_logmel: null pointer");
   SOME_REQUIRE(out_f32 || out_bf16, "some_mel_logmel: no output buffer");
   if (B <= 0 || max_frames <= 0) return 0;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};   // function attributes are per device
+  const int dev_ = device_index();
+  if (!configured[dev_]) {
     cudaError_t e = cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MEL_SMEM);
     SOME_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(mel): %s", cudaGetErrorString(e));
-    configured = true;
+    configured[dev_] = true;
   }
   const int tiles_per_clip = (max_frames + MEL_FPB - 1) / MEL_FPB;
   const long long grid = 1ll * tiles_per_clip * B;
   SOME_REQUIRE(grid < (1ll << 31), "some_mel_logmel: grid too large");
-  mel_kernel<<<static_cast<unsigned>(grid), 256, MEL_SMEM, stream>>>(
+  mel_kernel<<<static_cast<unsigned>(grid), MEL_WARPS * 32, MEL_SMEM, stream>>>(
       wave, clip_start, clip_len, cu_frames, tiles_per_clip, mel_start, mel_count, mel_weights, twiddle, window, out_f32,
       reinterpret_cast<__nv_bfloat16*>(out_bf16), clamp);
   return check_launch("some_mel_logmel");

@@ -103,6 +103,69 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
   }
 }
 
+// K-rowstats: bf16(x) and the full-row (sum x, sum x^2) in slot 0 of ln_stats, for a residual stream that no producer GEMM
+// has written yet (the input projection in front of block 0): the LayerNorm-folded consumer GEMMs then treat it like any
+// other producer output (some_gemm, SOME_EPI_LN_*; ln_parts = 1).  Same streaming structure as layernorm_kernel.
+struct RowStatsParams {
+  const float* x[2];
+  __nv_bfloat16* out_bf16[2];
+  float* stats[2];
+  int M;
+};
+__global__ void __launch_bounds__(256) row_stats_kernel(const RowStatsParams p) {
+  const int grp = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int row0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * LN_RPW;
+  if (row0 >= p.M) return;
+  float v[LN_RPW][16];
+#pragma unroll
+  for (int r = 0; r < LN_RPW; ++r)
+    if (row0 + r < p.M) ln_load(p.x[grp] + (size_t)(row0 + r) * D, lane, v[r]);
+#pragma unroll
+  for (int r = 0; r < LN_RPW; ++r) {
+    if (row0 + r < p.M) {
+      float s = 0.f, q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        s += v[r][i];
+        q = fmaf(v[r][i], v[r][i], q);
+      }
+      s = warp_sum(s);
+      q = warp_sum(q);
+      __nv_bfloat16* o = p.out_bf16[grp] + (size_t)(row0 + r) * D;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<uint2*>(o + 128 * i + 4 * lane) =
+            make_uint2(pack_bf16x2(v[r][4 * i], v[r][4 * i + 1]), pack_bf16x2(v[r][4 * i + 2], v[r][4 * i + 3]));
+      if (lane == 0)
+        reinterpret_cast<float2*>(p.stats[grp])[(size_t)(row0 + r) * SOME_LN_SLOTS] = make_float2(s, q);
+    }
+  }
+}
+
+// K-colmeans (calibration only, load time): column means of a GEMM's (effective) A operand.  One thread per column, rows
+// strided over blockIdx.y, partial sums combined with atomics into a zeroed buffer; the caller divides by M.
+__global__ void __launch_bounds__(128)
+col_means_kernel(const __nv_bfloat16* __restrict__ a, int M, int K, int lda, const float* __restrict__ stats, int parts,
+                 float inv_m, float* __restrict__ out) {
+  const int k = blockIdx.x * 128 + threadIdx.x;
+  if (k >= K) return;
+  float acc = 0.f;
+  for (int row = blockIdx.y; row < M; row += gridDim.y) {
+    float v = __bfloat162float(a[(size_t)row * lda + k]);
+    if (stats != nullptr) {
+      float s = 0.f, q = 0.f;
+      const float2* st = reinterpret_cast<const float2*>(stats) + (size_t)row * SOME_LN_SLOTS;
+      for (int i = 0; i < parts; ++i) s += st[i].x, q += st[i].y;
+      const float mean = s / K;
+      const float var = fmaxf(q / K - mean * mean, 0.f);
+      v = (v - mean) * rsqrtf(var + 1e-5f);
+    }
+    acc += v;
+  }
+  atomicAdd(out + k, acc * inv_m);
+}
+
 __global__ void __launch_bounds__(256)
 bound_head_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                   const float* __restrict__ w, float bias, int M, float* __restrict__ bounds) {
@@ -246,6 +309,35 @@ extern "C" int some_layernorm(const some_ln_args* a, cudaStream_t stream) {
   dim3 grid((a->M + 8 * LN_RPW - 1) / (8 * LN_RPW), a->groups);
   layernorm_kernel<<<grid, 256, 0, stream>>>(p);
   return check_launch("some_layernorm");
+}
+
+extern "C" int some_row_stats(const some_rowstats_args* a, cudaStream_t stream) {
+  SOME_REQUIRE(a != nullptr && (a->groups == 1 || a->groups == 2), "some_row_stats: bad args");
+  if (a->M <= 0) return 0;
+  RowStatsParams p;
+  for (int g = 0; g < 2; ++g) {
+    const int s = g < a->groups ? g : 0;
+    SOME_REQUIRE(a->x[s] && a->out_bf16[s] && a->ln_stats[s], "some_row_stats: null pointer in group %d", s);
+    p.x[g] = a->x[s];
+    p.out_bf16[g] = reinterpret_cast<__nv_bfloat16*>(a->out_bf16[s]);
+    p.stats[g] = a->ln_stats[s];
+  }
+  p.M = a->M;
+  dim3 grid((a->M + 8 * LN_RPW - 1) / (8 * LN_RPW), a->groups);
+  row_stats_kernel<<<grid, 256, 0, stream>>>(p);
+  return check_launch("some_row_stats");
+}
+
+extern "C" int some_col_means(const uint16_t* a, int M, int K, int lda, const float* ln_stats, int ln_parts, float* out,
+                              cudaStream_t stream) {
+  SOME_REQUIRE(a != nullptr && out != nullptr && M > 0 && K > 0 && K <= SOME_CALIB_K, "some_col_means: bad arguments");
+  SOME_REQUIRE(ln_stats == nullptr || (ln_parts >= 1 && ln_parts <= SOME_LN_SLOTS), "some_col_means: bad ln_parts");
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * K, stream);
+  SOME_REQUIRE(e == cudaSuccess, "some_col_means: %s", cudaGetErrorString(e));
+  dim3 grid((K + 127) / 128, M < 64 ? M : 64);
+  col_means_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a), M, K, lda, ln_stats, ln_parts,
+                                             1.0f / M, out);
+  return check_launch("some_col_means");
 }
 
 extern "C" int some_bound_head(const float* x, const float* gamma, const float* beta, const float* w, float bias,

@@ -91,6 +91,21 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 2-D tiled store shared -> global (bulk async-group completion).  The issuing THREAD owns the group: commit / wait must
+// be executed by the same thread.  Rows / columns of the box outside the tensor are clipped by the hardware.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// waits until at most kPending of this thread's committed bulk groups still READ their shared-memory source
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05: TMEM allocation
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {  // whole warp
@@ -265,6 +280,33 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mas
       : "memory");
 }
 
+// ------------------------------------------------------------------ packed f32x2 math (sm_100 FFMA2 / FADD2 / FMUL2)
+// One issue slot for two fp32 lanes held in an aligned register pair; the epilogues and the softmax are issue / latency
+// bound on a handful of warps, so halving the instruction count of their element-wise math is a direct win.
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 // ------------------------------------------------------------------ small math helpers
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
@@ -280,6 +322,24 @@ __device__ __forceinline__ float silu_fast(float x) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(uint64_t v2) {
+  float a, b;
+  f2_unpack(v2, a, b);
+  return pack_bf16x2(a, b);
+}
+// SiLU / sigmoid of a packed pair: the affine parts on the packed pipes, one MUFU.TANH per lane
+__device__ __forceinline__ uint64_t silu_fast2(uint64_t x2) {
+  const uint64_t h2 = f2_mul(x2, f2_pack(0.5f, 0.5f));
+  float h0, h1;
+  f2_unpack(h2, h0, h1);
+  return f2_fma(h2, f2_pack(tanh_approx(h0), tanh_approx(h1)), h2);
+}
+__device__ __forceinline__ uint64_t sigmoid_fast2(uint64_t x2) {
+  const uint64_t h2 = f2_mul(x2, f2_pack(0.5f, 0.5f));
+  float h0, h1;
+  f2_unpack(h2, h0, h1);
+  return f2_fma(f2_pack(tanh_approx(h0), tanh_approx(h1)), f2_pack(0.5f, 0.5f), f2_pack(0.5f, 0.5f));
 }
 
 }  // namespace some

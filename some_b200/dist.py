@@ -12,6 +12,7 @@ per-clip note records (a few KB..MB) so that every rank ends with the full, inpu
 """
 from __future__ import annotations
 
+import collections.abc
 from typing import Dict, List, Sequence
 
 import numpy as np
@@ -109,6 +110,41 @@ def gather_results(local: List[Dict[str, np.ndarray]], lengths: Sequence[int], s
     return merged
 
 
+class ShardedResults(collections.abc.Sequence):
+    """The ordered result list of a data-parallel infer: behaves like the ``List[Dict]`` of ``BaseInference.infer`` but
+    unpacks a rank's slab only when one of ITS clips is first touched — a caller that consumes only its own shard (or rank 0
+    writing the output files) never pays for converting world x clips note records on every rank."""
+
+    def __init__(self, n: int, owner: Sequence[int], unpackers):
+        self._items: List = [None] * n
+        self._owner = list(owner)              # clip index -> rank
+        self._unpackers = list(unpackers)      # rank -> callable() -> [(clip index, result dict), ...] or None once done
+
+    def _materialise_rank(self, r: int):
+        fn = self._unpackers[r]
+        if fn is not None:
+            self._unpackers[r] = None
+            for idx, res in fn():
+                self._items[idx] = res
+
+    def materialise(self) -> List[Dict[str, np.ndarray]]:
+        for r in range(len(self._unpackers)):
+            self._materialise_rank(r)
+        return self._items
+
+    def __len__(self):
+        return len(self._items)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self._items)
+        if self._items[i] is None and self._owner[i] >= 0:
+            self._materialise_rank(self._owner[i])
+        return self._items[i]
+
+
 def infer_sharded(plugin, waveforms: Sequence[np.ndarray], group=None) -> List[Dict[str, np.ndarray]]:
     """Data-parallel ``infer``: every rank holds the same ``waveforms`` list (or at least its own shard's
     entries), processes its shard and all ranks return the full ordered result list.
@@ -126,21 +162,33 @@ def infer_sharded(plugin, waveforms: Sequence[np.ndarray], group=None) -> List[D
         nbytes = max(16, max(l[2] for l in layouts))
         with getattr(plugin, '_lock', threading.Lock()), torch.cuda.device(eng.device):
             mine = [waveforms[i] for i in shards[rank]]
-            gathered = torch.empty(world * nbytes, dtype=torch.uint8, device=eng.device)
+            # persistent gather buffer (device) + page-locked landing buffer (host); the decode kernel writes this rank's
+            # notes STRAIGHT into its slot of the gather buffer and the collective runs in place (send = own slot)
+            buf = getattr(eng, '_gather', None)
+            if buf is None or buf[0].numel() < world * nbytes:
+                buf = (torch.empty(world * nbytes, dtype=torch.uint8, device=eng.device),
+                       torch.empty(world * nbytes, dtype=torch.uint8).pin_memory())
+                eng._gather = buf
+            gathered, landing = buf[0][:world * nbytes], buf[1][:world * nbytes]
             slot = gathered[rank * nbytes:(rank + 1) * nbytes]
             if mine:
-                slab, _, _, _ = eng.enqueue(mine, quantized=getattr(plugin, 'quantized', False))
-                slot[:slab.numel()].copy_(slab, non_blocking=True)
-            dist.all_gather_into_tensor(gathered, slot.clone(), group=group)
-            host = gathered.cpu().numpy()
-        merged: List[Dict[str, np.ndarray]] = [None] * len(lengths)  # type: ignore
-        for r in range(world):
+                eng.enqueue(mine, quantized=getattr(plugin, 'quantized', False), out=slot)
+            dist.all_gather_into_tensor(gathered, slot, group=group)
+            landing.copy_(gathered, non_blocking=True)
+            torch.cuda.current_stream(eng.device).synchronize()
+            host = landing.numpy().copy()      # the landing buffer is reused by the next call; 9 B / frame, a plain memcpy
+
+        def unpacker(r):
             cu_r, layout_r, _ = layouts[r]
-            if not layout_r:
-                continue
-            for idx, res in zip(shards[r], eng.unpack_slab(host[r * nbytes:(r + 1) * nbytes], cu_r, layout_r)):
-                merged[idx] = res
-        return merged
+            return lambda: list(zip(shards[r], eng.unpack_slab(host[r * nbytes:(r + 1) * nbytes], cu_r, layout_r)))
+
+        owner = [-1] * len(lengths)
+        for r, s in enumerate(shards):
+            for i in s:
+                owner[i] = r
+        out = ShardedResults(len(lengths), owner, [unpacker(r) if layouts[r][1] else None for r in range(world)])
+        out._materialise_rank(rank)            # this rank's own clips eagerly, the others on first touch
+        return out
     local = plugin.infer([waveforms[i] for i in shards[rank]])
     dev = getattr(eng, 'device', None) if dist.get_backend(group) == 'nccl' else None
     return gather_results(local, lengths, shards, plugin.timestep, device=dev, group=group)

@@ -3,15 +3,18 @@ libsome_b200.so in order on the current CUDA stream and unpacks the decoded note
 
 Equivalent to running the reference's batch-1 loop (inference/base_infer.py:46-53) once per clip:
 clips never interact (per-clip attention, per-clip zero-padded depthwise conv, per-clip decode).
-Launch sequence per conform_blocke (Gconform.py:56-63), both streams (midi / bound) in every launch:
-    LN1 -> GEMM(ffn1.ln1)+SiLU -> GEMM(ffn1.ln2)*0.5+x -> LN2 -> GEMM(to_q|to_kv) -> attention ->
-    GEMM(to_out)+x -> LN3 -> GEMM(pointwise_conv1)+GLU -> dwconv+BN+SiLU -> GEMM(pointwise_conv2)+x ->
-    LN4 -> GEMM(ffn2.ln1)+SiLU -> GEMM(ffn2.ln2)*0.5+x -> LN5
+The trunk is sequenced natively (csrc/forward.cu: some_forward); per conform_blocke (Gconform.py:56-63), both streams
+(midi / bound) in every launch, norm1..norm4 folded into the GEMMs around them (SOME_B200_LN_FOLD=0 restores the
+stand-alone LayerNorm launches):
+    GEMM(ffn1.ln1')+SiLU -> GEMM(ffn1.ln2)*0.5+x -> GEMM(to_q|to_kv') -> attention -> GEMM(to_out)+x ->
+    GEMM(pointwise_conv1')+GLU -> dwconv+BN+SiLU -> GEMM(pointwise_conv2)+x -> GEMM(ffn2.ln1')+SiLU ->
+    GEMM(ffn2.ln2)*0.5+x -> LN5
 The residual stream x is fp32 [M, 512]; GEMM operands are bf16; accumulation is fp32.
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -43,6 +46,8 @@ class _Workspace:
         self.h = torch.empty((2, m, FFN_DIM), dtype=bf, device=device)       # FFN hidden
         self.qkv = torch.empty((2, m, 3 * DIM), dtype=bf, device=device)
         self.g = torch.empty((2, m, DIM), dtype=bf, device=device)           # GLU out (dwconv in)
+        self.xb = torch.empty((2, m, DIM), dtype=bf, device=device)          # bf16 copy of x (LayerNorm-folded consumers)
+        self.ln_stats = torch.empty((2, m, _lib.LN_SLOTS, 2), dtype=f32, device=device)   # per-row partial (sum, sum sq)
         self.units = torch.empty((m, 80), dtype=bf, device=device)
         self.probs = torch.empty((m, outdim), dtype=f32, device=device)
         self.bounds = torch.empty((m,), dtype=f32, device=device)
@@ -54,6 +59,7 @@ class _Workspace:
         for s in range(2):
             c.x[s], c.a[s], c.h[s] = self.x[s].data_ptr(), self.a[s].data_ptr(), self.h[s].data_ptr()
             c.qkv[s], c.g[s] = self.qkv[s].data_ptr(), self.g[s].data_ptr()
+            c.xb[s], c.ln_stats[s] = self.xb[s].data_ptr(), self.ln_stats[s].data_ptr()
         c.units, c.probs, c.bounds = self.units.data_ptr(), self.probs.data_ptr(), self.bounds.data_ptr()
 
 
@@ -67,33 +73,122 @@ class Engine:
             raise _lib.SomeB200Error('some_b200 runs on CUDA devices only (sm_100a); there is no CPU path')
         self.quantized = False
         self.w = ModelWeights(state_dict, config, self.device)
-        self._cmodel, self._cmodel_keep = build_c_model(self.w)
+        self.ln_fold = os.environ.get('SOME_B200_LN_FOLD', '1') != '0'
+        self._cmodel, self._cmodel_keep = build_c_model(self.w, self.ln_fold)
         self.mel = mel_tables(config, self.device)
         self.outdim = config['midi_num_bins']
         self.timestep = config['hop_size'] / config['audio_sample_rate']
         self._ws: Optional[_Workspace] = None
         self.launches = 0
         self._sum_t2 = 0.0
-        # launches of one trunk pass: inln + (lay + 1) blocks x 15 + lay GLU mixes + (final LN + bound head - LN5) + head
-        self.trunk_launches = 1 + 15 * (self.w.lay + 1) + self.w.lay + 1 + 1
-        # optional per-kernel timing: name -> [(start_event, end_event, work)] where work = FLOPs (GEMM,
-        # attention) or algorithmic bytes (HBM-bound kernels); enabled by bench.py via start_profile()
+        # launches of one trunk pass: inln (+ row_stats) + (lay + 1) blocks x 11 (15 unfolded) + lay GLU mixes
+        # + (final LN + bound head instead of LN5) + head
+        self._count_trunk_launches()
+        # optional per-kernel timing (bench.py): CUDA events around every launch — the native sequencer records its own
+        # (some_profiler), the kernels launched from here (mel, decode) are bracketed by _mark()
         self.prof: Optional[dict] = None
+        self._cprof = None
+        self._corrected: set = set()
+        self.bias_correction = os.environ.get('SOME_B200_BIAS_CORRECTION', '1') != '0'
+        if self.bias_correction:
+            self.calibrate()
+
+    def _count_trunk_launches(self):
+        per_block = 11 if self.ln_fold else 15
+        self.trunk_launches = 1 + int(self.ln_fold) + per_block * (self.w.lay + 1) + self.w.lay + 1 + 1
+
+    def set_ln_fold(self, flag: bool):
+        """Switches between the LayerNorm-folded launch sequence and the stand-alone LayerNorm launches (tests, A/B)."""
+        self.ln_fold = bool(flag)
+        self._cmodel, self._cmodel_keep = build_c_model(self.w, self.ln_fold)
+        self._count_trunk_launches()
+
+    def calibrate(self, seconds: float = 4.0):
+        """Load-time bias correction for the bf16 rounding of the weights.  Rounding W to bf16 is a FIXED perturbation of the
+        model: its mean effect on a layer's output, (W - bf16(W)) . E[a], is a constant per output channel that survives to
+        the boundary probabilities as a systematic offset (measured +3.5e-4 on `bounds` with the seeded weights) and is then
+        integrated by the decoder's cumsum (utils/infer_utils.py:28) into a drift of about one note per 30 s clip.  The
+        standard post-training-quantisation remedy is applied here: one short calibration clip (a seeded synthetic sung-note
+        signal; with stand-alone LayerNorms the operand means are dominated by the LayerNorm biases and the positive mean of
+        SiLU outputs, i.e. by the weights, and white noise calibrates equally well; with folded LayerNorms the operand is the
+        normalised row itself and a voice-like signal matters: residual -7e-5 vs -1.5e-4) runs through the sequencer, which
+        records the column means of every GEMM's effective operand (some_forward, `calib`), and each layer's bias absorbs
+        (W_master - bf16(W)) . mean.  After it the mean error of `bounds` is ~3e-5 and zero-mean rounding noise remains."""
+        reg = getattr(self.w, 'rounding', None)
+        if reg is None:
+            return
+        dev = self.device
+        with torch.cuda.device(dev):
+            from .synth import synth_waveform
+            wave = synth_waveform(20240917, seconds=seconds, sr=self.config['audio_sample_rate'])
+            host, tables, cu = self.pack([wave])
+            m = int(cu[-1])
+            ws = self.workspace(m)
+            wave_d, tab_d, cu_d = host.to(dev), tables.to(dev), torch.from_numpy(cu).to(dev)
+            self.run_mel(wave_d, tab_d[:1], tab_d[1:], cu_d, 1, m, None, ws.units)
+            means = torch.zeros((_lib.CALIB_MAX, 2, _lib.CALIB_K), dtype=torch.float32, device=dev)
+            cal = _lib.CalibrationC()
+            cal.means = means.data_ptr()
+            # both launch sequences (LayerNorm-folded and not) so that every layer's bias is corrected exactly once,
+            # whichever mode is selected later (set_ln_fold)
+            for fold in (self.ln_fold, not self.ln_fold):
+                cmodel, keep = build_c_model(self.w, fold)
+                _lib.check(self.lib.some_forward(C.byref(cmodel), C.byref(ws.c), m, 1, cu_d.data_ptr(), m, _lib.EPI_BIAS_F32,
+                                                 None, C.byref(cal), self._stream), 'some_forward(calibration)')
+                torch.cuda.synchronize(dev)
+                for i in range(cal.count):
+                    k = cal.k[i]
+                    for s in range(2):
+                        ptr = cal.w[i][s]
+                        ent = reg.entries.get(ptr)
+                        if ent is None or ptr in self._corrected:
+                            continue
+                        self._corrected.add(ptr)
+                        master, rounded, bias = ent
+                        if bias is None:
+                            continue
+                        delta = (master.double() - rounded.double()) @ means[i, s, :k].double()
+                        bias[:delta.numel()] += delta.float()
+                del cmodel, keep
+        self.w.rounding = None                 # drop the fp32 masters
 
     def start_profile(self, cu_frames_host=None):
         self.prof = {}
         if cu_frames_host is not None:
             t = np.diff(np.asarray(cu_frames_host)).astype(np.float64)
             self._sum_t2 = float((t * t).sum())
+        if self._cprof is None:
+            h = C.c_void_p()
+            _lib.check(self.lib.some_profiler_create(1 << 14, C.byref(h)), 'some_profiler_create')
+            self._cprof = h
+        _lib.check(self.lib.some_profiler_reset(self._cprof), 'some_profiler_reset')
 
     def stop_profile(self) -> Dict[str, dict]:
-        """Returns {kernel: {launches, ms, work}} from the CUDA events recorded since start_profile()."""
+        """Returns {kernel: {launches, ms, work, shapes}} from the CUDA events recorded since start_profile(): the native
+        sequencer's records (some_profiler_read) plus the launches bracketed from Python (mel, decode)."""
         torch.cuda.synchronize(self.device)
         out = {}
         for name, recs in (self.prof or {}).items():
             out[name] = {'launches': len(recs), 'ms': float(sum(a.elapsed_time(b) for a, b, _ in recs)),
                          'work': float(sum(w for _, _, w in recs))}
         self.prof = None
+        cap = 1 << 14
+        recs = (_lib.ProfileRecord * cap)()
+        n = self.lib.some_profiler_read(self._cprof, cap, recs)
+        if n < 0:
+            _lib.check(n, 'some_profiler_read')
+        att_flops = float(2 * 2 * 2 * 512 * self._sum_t2)      # QK^T + PV, 8 heads x 64, both streams, 2 FLOP / MAC
+        for r in recs[:min(n, cap)]:
+            name = _lib.KERNEL_NAMES.get(r.kernel, f'kernel{r.kernel}')
+            d = out.setdefault(name, {'launches': 0, 'ms': 0.0, 'work': 0.0})
+            d['launches'] += 1
+            d['ms'] += float(r.ms)
+            d['work'] += att_flops if r.kernel == _lib.K_ATTENTION else float(r.work)
+            if r.kernel == _lib.K_GEMM:
+                sh = d.setdefault('shapes', {}).setdefault(f'epi{r.epilogue}_N{r.n}_K{r.k}', {'launches': 0, 'ms': 0.0, 'work': 0.0})
+                sh['launches'] += 1
+                sh['ms'] += float(r.ms)
+                sh['work'] += float(r.work)
         return out
 
     def _mark(self, name: str, work: float):
@@ -128,25 +223,6 @@ class Engine:
             self._ws = _Workspace(max(m, 1), self.outdim, self.device)
         return self._ws
 
-    def _gemm(self, a0, a1, w0, w1, b0, b1, out0, out1, r0, r1, m, n, k, lda, ld_out, epi, alpha=1.0, groups=2):
-        g = _lib.GemmArgs()
-        g.A, g.W = _lib.pair(a0, a1), _lib.pair(w0, w1)
-        g.bias, g.out, g.resid = _lib.pair(b0, b1), _lib.pair(out0, out1), _lib.pair(r0, r1)
-        g.groups, g.M, g.N, g.K, g.lda, g.ld_out, g.epilogue, g.alpha = groups, m, n, k, lda, ld_out, epi, alpha
-        with self._mark('some_gemm', 2.0 * m * n * k * groups):
-            _lib.check(self.lib.some_gemm(C.byref(g), self._stream), 'some_gemm')
-
-    def _ln(self, x, gamma, beta, out_bf16, out_f32, m):
-        a = _lib.LnArgs()
-        a.x = _lib.pair(x[0], x[1])
-        a.gamma, a.beta = _lib.pair(*gamma), _lib.pair(*beta)
-        a.out_bf16 = _lib.pair(out_bf16[0], out_bf16[1]) if out_bf16 is not None else (C.c_void_p * 2)()
-        a.out_f32 = _lib.pair(out_f32[0], out_f32[1]) if out_f32 is not None else (C.c_void_p * 2)()
-        a.groups, a.M = 2, m
-        nout = (2 if out_bf16 is not None else 0) + (4 if out_f32 is not None else 0)
-        with self._mark('some_layernorm', 2.0 * m * DIM * (4 + nout)):
-            _lib.check(self.lib.some_layernorm(C.byref(a), self._stream), 'some_layernorm')
-
     # ------------------------------------------------------------------ stages
     def run_mel(self, wave: torch.Tensor, clip_start: torch.Tensor, clip_len: torch.Tensor, cu_frames: torch.Tensor,
                 b: int, max_frames: int, out_f32: Optional[torch.Tensor], out_bf16: Optional[torch.Tensor]):
@@ -160,91 +236,16 @@ class Engine:
                 t['twiddle'].data_ptr(), t['window'].data_ptr(), _lib.ptr(out_f32), _lib.ptr(out_bf16),
                 1e-5, self._stream), 'some_mel_logmel')
 
-    def _block(self, ws: _Workspace, blk, m: int, b: int, cu_frames, max_frames: int, last: bool):
-        x, a, h, qkv, g = ws.x, ws.a, ws.h, ws.qkv, ws.g
-        lib, st = self.lib, self._stream
-        w0, w1 = blk
-
-        def ln(i, out_bf16=a, out_f32=None):
-            self._ln(x, (w0.ln_g[i], w1.ln_g[i]), (w0.ln_b[i], w1.ln_b[i]), out_bf16, out_f32, m)
-
-        def ffn(i):
-            f0, f1 = w0.ffn[i], w1.ffn[i]
-            self._gemm(a[0], a[1], f0['w1'], f1['w1'], f0['b1'], f1['b1'], h[0], h[1], None, None,
-                       m, FFN_DIM, DIM, DIM, FFN_DIM, _lib.EPI_SILU_BF16)
-            self._gemm(h[0], h[1], f0['w2'], f1['w2'], f0['b2'], f1['b2'], x[0], x[1], x[0], x[1],
-                       m, DIM, FFN_DIM, FFN_DIM, DIM, _lib.EPI_RESID_F32, alpha=0.5)
-
-        ln(0)
-        ffn(0)                                                                   # Gconform.py:57
-        ln(1)
-        self._gemm(a[0], a[1], w0.w_qkv, w1.w_qkv, None, None, qkv[0], qkv[1], None, None,
-                   m, 3 * DIM, DIM, DIM, 3 * DIM, _lib.EPI_STORE_BF16)
-        at = _lib.AttnArgs()
-        at.qkv, at.out = _lib.pair(qkv[0], qkv[1]), _lib.pair(a[0], a[1])
-        at.groups, at.B, at.M, at.cu_frames, at.max_frames = 2, b, m, cu_frames.data_ptr(), max_frames
-        with self._mark('some_attention_varlen', 2.0 * self._att_flops):
-            _lib.check(lib.some_attention_varlen(C.byref(at), st), 'some_attention_varlen')
-        self._gemm(a[0], a[1], w0.w_out, w1.w_out, w0.b_out, w1.b_out, x[0], x[1], x[0], x[1],
-                   m, DIM, DIM, DIM, DIM, _lib.EPI_RESID_F32)                   # :60
-        ln(2)
-        self._gemm(a[0], a[1], w0.w_pw1, w1.w_pw1, w0.b_pw1, w1.b_pw1, g[0], g[1], None, None,
-                   m, 2 * DIM, DIM, DIM, DIM, _lib.EPI_GLU_BF16)                # base_conv.py:65
-        dw = _lib.DwconvArgs()
-        dw.x, dw.w, dw.b = _lib.pair(g[0], g[1]), _lib.pair(w0.w_dw, w1.w_dw), _lib.pair(w0.b_dw, w1.b_dw)
-        dw.out = _lib.pair(a[0], a[1])
-        dw.groups, dw.B, dw.cu_frames, dw.max_frames = 2, b, cu_frames.data_ptr(), max_frames
-        with self._mark('some_dwconv_bn_silu', 2.0 * m * DIM * 4):               # bf16 in + bf16 out
-            _lib.check(lib.some_dwconv_bn_silu(C.byref(dw), st), 'some_dwconv_bn_silu')   # base_conv.py:66-68
-        self._gemm(a[0], a[1], w0.w_pw2, w1.w_pw2, w0.b_pw2, w1.b_pw2, x[0], x[1], x[0], x[1],
-                   m, DIM, DIM, DIM, DIM, _lib.EPI_RESID_F32)                   # base_conv.py:69 + Gconform.py:61
-        ln(3)
-        ffn(1)                                                                   # :62
-        if not last:
-            ln(4, out_bf16=a, out_f32=x)                                         # :63 (residual for the next Gcf)
-        else:
-            # final pair: midi stream -> normalised bf16 for outln; bound stream -> fused norm5 + cutheard + sigmoid
-            al = _lib.LnArgs()
-            al.x, al.gamma, al.beta = _lib.pair(x[0]), _lib.pair(w0.ln_g[4]), _lib.pair(w0.ln_b[4])
-            al.out_bf16, al.out_f32 = _lib.pair(a[0]), (C.c_void_p * 2)()
-            al.groups, al.M = 1, m
-            with self._mark('some_layernorm', m * DIM * 6.0):
-                _lib.check(lib.some_layernorm(C.byref(al), st), 'some_layernorm')
-            with self._mark('some_bound_head', m * DIM * 4.0):
-                _lib.check(lib.some_bound_head(x[1].data_ptr(), w1.ln_g[4].data_ptr(), w1.ln_b[4].data_ptr(),
-                                               self.w.w_cut.data_ptr(), self.w.b_cut, m, ws.bounds.data_ptr(), st),
-                           'some_bound_head')
-
     def run_trunk(self, ws: _Workspace, m: int, b: int, cu_frames: torch.Tensor, max_frames: int,
-                  head: str = 'sigmoid', taps: Optional[dict] = None):
+                  head: str = 'sigmoid'):
         """Gmidi_conform.forward (Gconform.py:119-140) + the head activation of midi_conforms.forward
-        (Gmidi_conform.py:30-40).  Reads ws.units; writes ws.probs [m, outdim] and ws.bounds [m].
-        head: 'sigmoid' | 'softmax' | 'logits'."""
-        w, x, a = self.w, ws.x, ws.a
+        (Gmidi_conform.py:30-40): ONE native call enqueues the whole launch sequence (csrc/forward.cu).
+        Reads ws.units; writes ws.probs [m, outdim] and ws.bounds [m].  head: 'sigmoid' | 'softmax' | 'logits'."""
         epi = {'sigmoid': _lib.EPI_SIGMOID_F32, 'softmax': _lib.EPI_SOFTMAX_F32, 'logits': _lib.EPI_BIAS_F32}[head]
-        if self.prof is None and taps is None:
-            # product path: one native call enqueues the whole launch sequence (csrc/forward.cu)
-            _lib.check(self.lib.some_forward(C.byref(self._cmodel), C.byref(ws.c), m, b, cu_frames.data_ptr(), max_frames,
-                                             epi, self._stream), 'some_forward')
-            self.launches += self.trunk_launches
-            return
-        # per-kernel path (CUDA events around every launch / intermediate taps): same sequence, driven from Python
-        # QK^T + PV MACs of one attention launch (both streams): 2 * 8 heads * 64 * sum T^2 (profiling only; the clip
-        # lengths come from the host copy of cu_frames so that no device sync sneaks into the timed region)
-        self._att_flops = float(2 * 2 * 512 * self._sum_t2) if self.prof is not None else 0.0
-        self._gemm(ws.units, ws.units, w.w_in[0], w.w_in[1], w.b_in[0], w.b_in[1], x[0], x[1], None, None,
-                   m, DIM, 80, 80, DIM, _lib.EPI_BIAS_F32)                       # inln / inln1
-        for i in range(w.lay):
-            self._block(ws, w.blocks[i], m, b, cu_frames, max_frames, last=False)
-            # Gcf.forward :85-87: midi += GLU(glu2(bound)); bound += GLU(glu1(midi))  (a = bf16 copies of norm5 out)
-            self._gemm(a[1], a[0], w.glu_w[i][1], w.glu_w[i][0], w.glu_b[i][1], w.glu_b[i][0],
-                       x[0], x[1], x[0], x[1], m, 2 * DIM, DIM, DIM, DIM, _lib.EPI_GLU_RESID_F32)
-            if taps is not None:
-                taps[f'model.cf_lay.{i}:midi'] = x[0, :m].clone()
-                taps[f'model.cf_lay.{i}:bound'] = x[1, :m].clone()
-        self._block(ws, w.blocks[w.lay], m, b, cu_frames, max_frames, last=True)
-        self._gemm(a[0], None, w.w_head, None, w.b_head, None, ws.probs, None, None, None,
-                   m, self.outdim, DIM, DIM, self.outdim, epi, groups=1)          # outln (+ sigmoid / softmax)
+        prof = self._cprof if self.prof is not None else None
+        _lib.check(self.lib.some_forward(C.byref(self._cmodel), C.byref(ws.c), m, b, cu_frames.data_ptr(), max_frames,
+                                         epi, prof, None, self._stream), 'some_forward')
+        self.launches += self.trunk_launches
 
     def run_decode(self, ws: _Workspace, m: int, b: int, cu_frames: torch.Tensor, note_count: torch.Tensor,
                    quantized: bool, dbg: Optional[dict] = None, probs=None, bounds=None, out=None):
@@ -268,6 +269,7 @@ class Engine:
         d.scratch = ws.scratch.data_ptr()
         with self._mark('some_decode_notes', m * (self.outdim * 4.0 + 4.0)):
             _lib.check(self.lib.some_decode_notes(C.byref(d), self._stream), 'some_decode_notes')
+        self.launches += 2                     # frames + align + notes kernels behind the one call
 
     # ------------------------------------------------------------------ public batched entry point
     def tables(self, lens: np.ndarray):
@@ -303,6 +305,8 @@ class Engine:
                 'wave_d': torch.empty(cap_w, dtype=torch.float32, device=self.device),
                 'tab_h': torch.empty(cap_b, dtype=torch.int64).pin_memory(),
                 'tab_d': torch.empty(cap_b, dtype=torch.int64, device=self.device),
+                'cu_h': torch.empty(cap_b, dtype=torch.int32).pin_memory(),       # per-chunk cu_frames, staged as int32
+                'cu_d': torch.empty(cap_b, dtype=torch.int32, device=self.device),
                 'out_h': torch.empty(cap_o, dtype=torch.uint8).pin_memory(),
                 'out_d': torch.empty(cap_o, dtype=torch.uint8, device=self.device),
             }
@@ -352,10 +356,18 @@ class Engine:
         return cu, layout, off
 
     def enqueue(self, waveforms: Sequence[np.ndarray], quantized: bool = False, return_intermediates: bool = False,
-                resident=None):
+                resident=None, out: Optional[torch.Tensor] = None):
         """Stages, copies and enqueues the whole batch WITHOUT synchronising.  Returns (device slab uint8 [nbytes], cu, layout,
         extra): the decoded notes land in the device slab (see slab_layout); the caller copies it to the host (infer) or
         hands it to the all-gather (dist.infer_sharded).
+
+        ``out``: optional device uint8 buffer (16-byte aligned, >= the slab size) the decode kernel writes the slab into instead
+        of the engine's own — dist.infer_sharded passes this rank's slot of the all-gather buffer, so the notes go from the
+        decode kernel to the collective without a staging copy.
+
+        Contract: the engine owns ONE set of staging / slab buffers.  A second enqueue() may only be issued after the consumer
+        of the previous one has synchronised (or waited on the stream): infer(), infer_sliced(), dist.infer_sharded() and the
+        dataset driver all do.  The call itself first makes the copy stream wait for everything enqueued so far.
 
         ``resident = (wave_d, ranges)``: the audio is already on the device (f32 tensor) and the clips are the sample ranges
         ``[(begin, end), ...]`` inside it (``waveforms`` is ignored): no staging, no audio H2D — the slicer path
@@ -382,8 +394,13 @@ class Engine:
         if getattr(self, '_copy_stream', None) is None:
             self._copy_stream = torch.cuda.Stream(dev)
         copy_stream = self._copy_stream
+        if getattr(self, '_h2d_done', None) is not None:
+            self._h2d_done.synchronize()      # the previous call's H2D copies have finished READING the pinned staging buffers
         copy_stream.wait_stream(stream)       # previous users of the staging / device buffers are done
         wave_h, wave_d, tab_h, tab_d, out_d = (st[k] for k in ('wave_h', 'wave_d', 'tab_h', 'tab_d', 'out_d'))
+        if out is not None:
+            assert out.dtype == torch.uint8 and out.is_cuda and out.numel() >= nbytes_total and out.data_ptr() % 16 == 0
+            out_d = out
         if resident is not None:
             wave_d = wave_res
             direct = []
@@ -404,7 +421,8 @@ class Engine:
 
         ws = self.workspace(max(mc for *_, mc in layout))
         extra = None
-        for c0, c1, out_off, bc, mc in layout:
+        cu_h, cu_dev = st['cu_h'], st['cu_d']
+        for ci, (c0, c1, out_off, bc, mc) in enumerate(layout):
             lo = int(starts[c0])
             todo = []
             if resident is None:
@@ -413,11 +431,13 @@ class Engine:
                     list(pool.map(stage, todo))
                 hi = int(starts[c1 - 1] + ((lens[c1 - 1] + 3) & ~3))
             # var-len tables of this chunk, relative to its own first sample / first frame
-            tab = tab_h[4 * c0:4 * c0 + 3 * bc + 1]
+            tab = tab_h[2 * c0:2 * c0 + 2 * bc]
             tab[:bc] = torch.from_numpy(starts[c0:c1] - lo)
             tab[bc:2 * bc] = torch.from_numpy(lens[c0:c1])
-            tab[2 * bc:3 * bc + 1] = torch.from_numpy((cu[c0:c1 + 1] - cu[c0]).astype(np.int64))
-            tab_dev = tab_d[4 * c0:4 * c0 + 3 * bc + 1]
+            tab_dev = tab_d[2 * c0:2 * c0 + 2 * bc]
+            cu_c = cu_h[c0 + ci:c1 + ci + 1]                 # chunk ci owns entries [c0 + ci, c1 + ci]: no overlap
+            cu_c.copy_(torch.from_numpy(cu[c0:c1 + 1] - cu[c0]))
+            cu_d = cu_dev[c0 + ci:c1 + ci + 1]
             with torch.cuda.stream(copy_stream):
                 if resident is not None:
                     pass
@@ -431,10 +451,10 @@ class Engine:
                             src = torch.from_numpy(waveforms[i]) if direct[i] else wave_h[starts[i]:starts[i] + n]
                             wave_d[starts[i]:starts[i] + n].copy_(src, non_blocking=True)
                 tab_dev.copy_(tab, non_blocking=True)
+                cu_d.copy_(cu_c, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
             stream.wait_event(ev)
-            cu_d = tab_dev[2 * bc:3 * bc + 1].to(torch.int32)
             max_frames = int(np.diff(cu[c0:c1 + 1]).max())
             # decode writes straight into this chunk's slab
             o = out_d[out_off:out_off + 4 * bc + 9 * mc]
@@ -448,6 +468,7 @@ class Engine:
             self.run_decode(ws, mc, bc, cu_d, note_count, quantized, out=(note_midi, note_dur, note_rest))
             if return_intermediates:
                 extra = (mel_f32, ws.probs[:mc], ws.bounds[:mc])
+        self._h2d_done = ev if layout else None
         return out_d[:nbytes_total], cu, layout, extra
 
     def rms_frames(self, wave_d: torch.Tensor, frame_length: int, hop: int) -> np.ndarray:

@@ -7,6 +7,9 @@
   and its gate land in the same 32-column chunk of the GEMM epilogue;
 * BatchNorm1d (eval, eps 1e-5) folded into the depthwise taps: w' = w * g / sqrt(var + eps),
   b' = (b - mean) * g / sqrt(var + eps) + beta  (base_conv.py:66-67);
+* LayerNorm folding (norm1..norm4 of every conform_blocke, Gconform.py:57-62): for the Linear behind each of them
+  W' = bf16(W * gamma), s = row sums of W', b' = bias + W . beta, so that  LN(x) . W^T + bias = rstd * (bf16(x) . W'^T -
+  mean * s) + b'  is evaluated in the consumer GEMM's epilogue (csrc/gemm.cu, SOME_EPI_LN_*);
 * mel filterbank (librosa htk / slaney, spec.py:22-28) as per-filter contiguous bin ranges, periodic
   Hann window and double-precision FFT twiddles.
 """
@@ -62,20 +65,15 @@ def mel_tables(config: dict, device) -> Dict[str, torch.Tensor]:
                 f'({_lib.MEL_BINS} bins, {_lib.MEL_MAXW} per filter); fmin/fmax/sr differ from the shipped configs')
         start[m], count[m] = lo, hi - lo + 1
         weights[m, :hi - lo + 1] = bank[m, lo:hi + 1]
-    # twiddles of the in-place radix-4 DIF FFT (mel.cu): per stage s (group length L = 1024 / 4^s, q = L / 4) the
-    # factors exp(-2 pi i m j / L), m = 1..3, j < q, contiguous in j; then exp(-2 pi i k / 2048) for the real-FFT unpack
-    parts = []
-    for st in range(4):
-        L = 1024 >> (2 * st)
-        q = L // 4
-        for mm in (1, 2, 3):
-            ang = -2.0 * np.pi * mm * np.arange(q, dtype=np.float64) / L
-            parts.append(np.stack([np.cos(ang), np.sin(ang)], axis=1))
+    # twiddles of the 32 x 32 register FFT (mel.cu): W_1024^(n2 k1) at [k1 * 32 + n2] (between the two 32-point passes),
+    # then W_2048^k for the real-FFT unpack of bins k < 372; computed in double
+    k1, n2 = np.meshgrid(np.arange(32, dtype=np.float64), np.arange(32, dtype=np.float64), indexing='ij')
+    ang = -2.0 * np.pi * (k1 * n2).reshape(-1) / 1024.0
+    parts = [np.stack([np.cos(ang), np.sin(ang)], axis=1)]
     ang = -2.0 * np.pi * np.arange(_lib.MEL_BINS, dtype=np.float64) / 2048.0
     parts.append(np.stack([np.cos(ang), np.sin(ang)], axis=1))
     tw = np.concatenate(parts, axis=0).astype(np.float32)
     assert tw.shape == (_lib.MEL_TW, 2)
-    n = np.arange(n_fft, dtype=np.float64)
     window = torch.hann_window(n_fft, periodic=True, dtype=torch.float32)    # spec.py:45 torch.hann_window
     return {
         'mel_start': torch.from_numpy(start).to(device),
@@ -103,30 +101,68 @@ def _pad32(v: torch.Tensor) -> torch.Tensor:
     return torch.cat([v, v.new_zeros(pad)]) if pad else v
 
 
+class RoundingRegistry:
+    """bf16 weight tensor (by device pointer) -> (fp32 master of exactly what was rounded, the bias tensor of that layer).
+    Filled while the checkpoint is packed, consumed once by Engine.calibrate() (bias correction for the weight rounding:
+    bias += (W - bf16(W)) . E[a]), then dropped."""
+
+    def __init__(self, device):
+        self.device = device
+        self.entries: Dict[int, tuple] = {}
+
+    def round(self, master: torch.Tensor, bias=None) -> torch.Tensor:
+        master = master.to(device=self.device, dtype=torch.float32).contiguous()
+        w = master.to(torch.bfloat16).contiguous()
+        self.entries[w.data_ptr()] = (master, w, bias)
+        return w
+
+    def attach_bias(self, w: torch.Tensor, bias: torch.Tensor):
+        m, ww, _ = self.entries[w.data_ptr()]
+        self.entries[w.data_ptr()] = (m, ww, bias)
+
+
 class BlockWeights:
     """Device tensors of one conform_blocke (Gconform.py:37-63)."""
 
-    def __init__(self, sd, p: str, device):
-        bf = lambda t: t.to(device=device, dtype=torch.bfloat16).contiguous()
+    def __init__(self, sd, p: str, device, reg: 'RoundingRegistry'):
         f32 = lambda t: t.to(device=device, dtype=torch.float32).contiguous()
+
+        def bf(t, bias=None):
+            return reg.round(t, bias)
+
         self.ln_g = [f32(sd[f'{p}.norm{i}.weight']) for i in range(1, 6)]
         self.ln_b = [f32(sd[f'{p}.norm{i}.bias']) for i in range(1, 6)]
         self.ffn = []
         for name in ('ffn1', 'ffn2'):
-            self.ffn.append(dict(w1=bf(sd[f'{p}.{name}.ln1.weight']), b1=f32(sd[f'{p}.{name}.ln1.bias']),
-                                 w2=bf(sd[f'{p}.{name}.ln2.weight']), b2=f32(sd[f'{p}.{name}.ln2.bias'])))
-        self.w_qkv = bf(torch.cat([sd[f'{p}.att.to_q.weight'], sd[f'{p}.att.to_kv.weight']], dim=0))
-        self.w_out = bf(sd[f'{p}.att.to_out.0.weight'])
+            b1, b2 = f32(sd[f'{p}.{name}.ln1.bias']), f32(sd[f'{p}.{name}.ln2.bias'])
+            self.ffn.append(dict(w1=bf(sd[f'{p}.{name}.ln1.weight'], b1), b1=b1, w2=bf(sd[f'{p}.{name}.ln2.weight'], b2), b2=b2))
+        self.w_qkv = bf(torch.cat([sd[f'{p}.att.to_q.weight'], sd[f'{p}.att.to_kv.weight']], dim=0))   # no bias to correct
         self.b_out = f32(sd[f'{p}.att.to_out.0.bias'])
-        self.w_pw1 = bf(glu_pack_rows(sd[f'{p}.conv.pointwise_conv1.weight'][:, :, 0]))
+        self.w_out = bf(sd[f'{p}.att.to_out.0.weight'], self.b_out)
         self.b_pw1 = f32(glu_pack_rows(sd[f'{p}.conv.pointwise_conv1.bias']))
+        self.w_pw1 = bf(glu_pack_rows(sd[f'{p}.conv.pointwise_conv1.weight'][:, :, 0]), self.b_pw1)
         scale = sd[f'{p}.conv.norm.weight'].double() / torch.sqrt(sd[f'{p}.conv.norm.running_var'].double() + BN_EPS)
         dw = sd[f'{p}.conv.depthwise_conv.weight'][:, 0, :].double()            # [C, K]
         self.w_dw = f32((dw * scale[:, None]).t())                              # [K, C]
         self.b_dw = f32((sd[f'{p}.conv.depthwise_conv.bias'].double() - sd[f'{p}.conv.norm.running_mean'].double())
                         * scale + sd[f'{p}.conv.norm.bias'].double())
-        self.w_pw2 = bf(sd[f'{p}.conv.pointwise_conv2.weight'][:, :, 0])
         self.b_pw2 = f32(sd[f'{p}.conv.pointwise_conv2.bias'])
+        self.w_pw2 = bf(sd[f'{p}.conv.pointwise_conv2.weight'][:, :, 0], self.b_pw2)
+
+        # ---- LayerNorm-folded consumers: (norm index, weight [N, 512], bias or None) -> (W' bf16, s f32, b' f32)
+        def fold(i, w, b, pack=lambda t: t):
+            g64, b64 = sd[f'{p}.norm{i}.weight'].double(), sd[f'{p}.norm{i}.bias'].double()
+            w64 = w.double()
+            bias = f32(pack((w64 @ b64 + (b.double() if b is not None else 0.0)).float()))
+            wf = bf(pack((w64 * g64[None, :]).float()), bias)
+            s_col = wf.double().sum(dim=1)                           # sums of the ROUNDED operand the tensor core sees
+            return wf, f32(s_col), bias
+
+        self.ffn_fold = [fold(1, sd[f'{p}.ffn1.ln1.weight'], sd[f'{p}.ffn1.ln1.bias']),
+                         fold(4, sd[f'{p}.ffn2.ln1.weight'], sd[f'{p}.ffn2.ln1.bias'])]
+        self.qkv_fold = fold(2, torch.cat([sd[f'{p}.att.to_q.weight'], sd[f'{p}.att.to_kv.weight']], dim=0), None)
+        self.pw1_fold = fold(3, sd[f'{p}.conv.pointwise_conv1.weight'][:, :, 0], sd[f'{p}.conv.pointwise_conv1.bias'],
+                             pack=glu_pack_rows)
 
 
 class ModelWeights:
@@ -136,26 +172,28 @@ class ModelWeights:
         args = config['midi_extractor_args']
         self.lay = args['lay']
         self.outdim = config['midi_num_bins']
-        bf = lambda t: t.to(device=device, dtype=torch.bfloat16).contiguous()
+        self.rounding = reg = RoundingRegistry(device)      # dropped by Engine.calibrate()
+        bf = reg.round
         f32 = lambda t: t.to(device=device, dtype=torch.float32).contiguous()
-        self.w_in = [bf(sd['model.inln.weight']), bf(sd['model.inln1.weight'])]
         self.b_in = [f32(sd['model.inln.bias']), f32(sd['model.inln1.bias'])]
+        self.w_in = [bf(sd['model.inln.weight'], self.b_in[0]), bf(sd['model.inln1.weight'], self.b_in[1])]
         self.blocks: List[List[BlockWeights]] = []      # [lay + 1][2]
         self.glu_w, self.glu_b = [], []                 # [lay][2]: index 0 = glu1 (fed by midi), 1 = glu2 (fed by bound)
         for i in range(self.lay):
             p = f'model.cf_lay.{i}'
-            self.blocks.append([BlockWeights(sd, p + '.att1', device), BlockWeights(sd, p + '.att2', device)])
-            self.glu_w.append([bf(glu_pack_rows(sd[p + '.glu1.0.weight'])), bf(glu_pack_rows(sd[p + '.glu2.0.weight']))])
+            self.blocks.append([BlockWeights(sd, p + '.att1', device, reg), BlockWeights(sd, p + '.att2', device, reg)])
             self.glu_b.append([f32(glu_pack_rows(sd[p + '.glu1.0.bias'])), f32(glu_pack_rows(sd[p + '.glu2.0.bias']))])
-        self.blocks.append([BlockWeights(sd, 'model.att1', device), BlockWeights(sd, 'model.att2', device)])
-        self.w_head = bf(sd['model.outln.weight'])                       # [outdim, 512]
+            self.glu_w.append([bf(glu_pack_rows(sd[p + '.glu1.0.weight']), self.glu_b[-1][0]),
+                               bf(glu_pack_rows(sd[p + '.glu2.0.weight']), self.glu_b[-1][1])])
+        self.blocks.append([BlockWeights(sd, 'model.att1', device, reg), BlockWeights(sd, 'model.att2', device, reg)])
         self.b_head = f32(_pad32(sd['model.outln.bias']))
+        self.w_head = bf(sd['model.outln.weight'], self.b_head)          # [outdim, 512]
         self.w_cut = f32(sd['model.cutheard.weight'][0])                 # [512]
         self.b_cut = float(sd['model.cutheard.bias'][0])
         assert self.w_in[0].shape == (DIM, config['units_dim'])
 
 
-def build_c_model(w: ModelWeights):
+def build_c_model(w: ModelWeights, ln_fold: bool = True):
     """ctypes mirror (include/some_b200.h: some_model) of the packed weights for the native launch sequencer
     some_forward.  Returns (ModelC, keepalive): the struct only holds raw pointers, `keepalive` owns the arrays."""
     import ctypes as C
@@ -174,6 +212,10 @@ def build_c_model(w: ModelWeights):
             b.w_pw1, b.b_pw1 = bw.w_pw1.data_ptr(), bw.b_pw1.data_ptr()
             b.w_dw, b.b_dw = bw.w_dw.data_ptr(), bw.b_dw.data_ptr()
             b.w_pw2, b.b_pw2 = bw.w_pw2.data_ptr(), bw.b_pw2.data_ptr()
+            for k in range(2):
+                b.ffn_w1f[k], b.ffn_s1[k], b.ffn_b1f[k] = (t.data_ptr() for t in bw.ffn_fold[k])
+            b.w_qkvf, b.s_qkv, b.b_qkvf = (t.data_ptr() for t in bw.qkv_fold)
+            b.w_pw1f, b.s_pw1, b.b_pw1f = (t.data_ptr() for t in bw.pw1_fold)
     n_glu = max(w.lay * 2, 1)
     glu_w = (C.c_void_p * n_glu)()
     glu_b = (C.c_void_p * n_glu)()
@@ -189,4 +231,5 @@ def build_c_model(w: ModelWeights):
     m.glu_w = C.cast(glu_w, C.POINTER(C.c_void_p))
     m.glu_b = C.cast(glu_b, C.POINTER(C.c_void_p))
     m.w_head, m.b_head, m.w_cut, m.b_cut = w.w_head.data_ptr(), w.b_head.data_ptr(), w.w_cut.data_ptr(), w.b_cut
+    m.ln_fold = int(bool(ln_fold))
     return m, (blocks, glu_w, glu_b)

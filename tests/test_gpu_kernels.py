@@ -113,6 +113,121 @@ def test_gemm_glu_epilogues(lib):
     torch.testing.assert_close(x, ref2, atol=3e-3, rtol=1e-3)
 
 
+def test_gemm_resid_out_of_place_and_ragged_rows(lib):
+    """TMA residual epilogue: resid != out, M not a multiple of 32 (clipped rows must stay untouched)."""
+    torch.manual_seed(21)
+    m, n, k = 1001, 512, 512
+    A = torch.randn(m, k, device=DEV).to(torch.bfloat16)
+    W = (torch.randn(n, k, device=DEV) / k ** 0.5).to(torch.bfloat16)
+    b = torch.randn(n, device=DEV)
+    x = torch.randn(m, n, device=DEV)
+    out = torch.full((m + 40, n), 7.0, device=DEV)           # 40 guard rows behind the tensor
+    run_gemm(lib, [A], [W], [b], [out[:m]], [x], _lib.EPI_RESID_F32)
+    torch.testing.assert_close(out[:m], A.float() @ W.float().t() + b + x, atol=2e-4, rtol=1e-4)
+    assert bool((out[m:] == 7.0).all()), 'rows beyond M were written'
+
+
+def run_gemm_ln(lib, A, W, bias, out, epi, ln_s=None, stats=None, parts=0, resid=None, out_bf16=None, alpha=1.0):
+    g = _lib.GemmArgs()
+    g.A, g.W, g.bias, g.out = _lib.pair(*A), _lib.pair(*W), _lib.pair(*bias), _lib.pair(*out)
+    g.resid = _lib.pair(*resid) if resid is not None else (C.c_void_p * 2)()
+    g.ln_s = _lib.pair(*ln_s) if ln_s is not None else (C.c_void_p * 2)()
+    g.ln_stats = _lib.pair(*stats) if stats is not None else (C.c_void_p * 2)()
+    g.out_bf16 = _lib.pair(*out_bf16) if out_bf16 is not None else (C.c_void_p * 2)()
+    g.ln_parts = parts
+    g.groups, g.M, g.K, g.N = len(A), A[0].shape[0], A[0].shape[1], W[0].shape[0]
+    g.lda, g.ld_out, g.epilogue, g.alpha = A[0].stride(0), out[0].stride(0), epi, alpha
+    _lib.check(lib.some_gemm(C.byref(g), stream()), 'some_gemm')
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize('glu', [False, True])
+def test_gemm_ln_producer(lib, glu):
+    """SOME_EPI_RESID_F32_LN / SOME_EPI_GLU_RESID_F32_LN: same out as the plain residual epilogue + bf16(out) + per-row partial
+    (sum x, sum x^2) in the slots of ln_stats (4 slots for N = 512, 8 for the GLU mix)."""
+    from some_b200.weights import glu_pack_rows
+    torch.manual_seed(22 + glu)
+    m, c, k = 777, 512, 512
+    groups = 2
+    A = [torch.randn(m, k, device=DEV).to(torch.bfloat16) for _ in range(groups)]
+    n = 2 * c if glu else c
+    W = [(torch.randn(n, k, device=DEV) / k ** 0.5).to(torch.bfloat16) for _ in range(groups)]
+    b = [torch.randn(n, device=DEV) for _ in range(groups)]
+    x = [torch.randn(m, c, device=DEV) * 2 + 0.7 for _ in range(groups)]
+    ref = []
+    for i in range(groups):
+        y = A[i].float() @ W[i].float().t() + b[i]
+        ref.append(x[i] + (y[:, :c] * torch.sigmoid(y[:, c:]) if glu else 0.5 * y))
+    Wk = [glu_pack_rows(w).contiguous() for w in W] if glu else W
+    bk = [glu_pack_rows(v).contiguous() for v in b] if glu else b
+    xb = [torch.full((m, c), float('nan'), device=DEV, dtype=torch.bfloat16) for _ in range(groups)]
+    stats = [torch.full((m, _lib.LN_SLOTS, 2), float('nan'), device=DEV) for _ in range(groups)]
+    run_gemm_ln(lib, A, Wk, bk, x, _lib.EPI_GLU_RESID_F32_LN if glu else _lib.EPI_RESID_F32_LN, stats=stats, resid=x,
+                out_bf16=xb, alpha=1.0 if glu else 0.5)
+    parts = 8 if glu else 4
+    for i in range(groups):
+        torch.testing.assert_close(x[i], ref[i], atol=3e-3 if glu else 2e-4, rtol=1e-3)
+        assert torch.equal(xb[i], x[i].to(torch.bfloat16)), 'out_bf16 is not the bf16 rounding of out'
+        st = stats[i][:, :parts]
+        assert not torch.isnan(st).any()
+        width = c // parts
+        cols = x[i].reshape(m, parts, width)
+        torch.testing.assert_close(st[:, :, 0], cols.sum(-1), atol=1e-3, rtol=1e-5)
+        torch.testing.assert_close(st[:, :, 1], (cols * cols).sum(-1), atol=1e-2, rtol=1e-5)
+
+
+@pytest.mark.parametrize('kind,parts', [('store', 4), ('silu', 1), ('glu', 8)])
+def test_gemm_ln_consumer(lib, kind, parts):
+    """SOME_EPI_LN_*: LayerNorm(x) . W^T + bias evaluated from bf16(x), W' = W * gamma, ln_s, b' and the partial row sums."""
+    from some_b200.weights import glu_pack_rows
+    torch.manual_seed(30 + parts)
+    m, k = 1000, 512
+    n = {'store': 1536, 'silu': 2048, 'glu': 1024}[kind]
+    x = [torch.randn(m, k, device=DEV) * 1.7 + 0.4 for _ in range(2)]
+    gamma = [torch.rand(k, device=DEV) * 0.4 + 0.8 for _ in range(2)]
+    beta = [torch.randn(k, device=DEV) * 0.05 for _ in range(2)]
+    W = [torch.randn(n, k, device=DEV) / k ** 0.5 for _ in range(2)]
+    b = [torch.randn(n, device=DEV) for _ in range(2)]
+    pack = glu_pack_rows if kind == 'glu' else (lambda t: t)
+    xb, Wf, s, bf, stats, ref = [], [], [], [], [], []
+    for i in range(2):
+        xb.append(x[i].to(torch.bfloat16))
+        wf = pack(W[i] * gamma[i][None, :]).to(torch.bfloat16).contiguous()
+        Wf.append(wf)
+        s.append(wf.double().sum(1).float().contiguous())
+        bf.append(pack((W[i].double() @ beta[i].double() + b[i].double()).float()).contiguous())
+        st = torch.full((m, _lib.LN_SLOTS, 2), float('nan'), device=DEV)
+        cols = x[i].reshape(m, parts, k // parts)
+        st[:, :parts, 0], st[:, :parts, 1] = cols.sum(-1), (cols * cols).sum(-1)
+        stats.append(st)
+        y = torch.nn.functional.layer_norm(x[i], (k,), gamma[i], beta[i], 1e-5) @ W[i].t() + b[i]
+        ref.append({'store': y, 'silu': torch.nn.functional.silu(y), 'glu': y[:, :n // 2] * torch.sigmoid(y[:, n // 2:])}[kind])
+    nout = n // 2 if kind == 'glu' else n
+    out = [torch.full((m, nout), float('nan'), device=DEV, dtype=torch.bfloat16) for _ in range(2)]
+    epi = {'store': _lib.EPI_LN_STORE_BF16, 'silu': _lib.EPI_LN_SILU_BF16, 'glu': _lib.EPI_LN_GLU_BF16}[kind]
+    run_gemm_ln(lib, xb, Wf, bf, out, epi, ln_s=s, stats=stats, parts=parts)
+    for i in range(2):
+        # bf16 operands (x and W * gamma) + bf16 output against the fp32 LayerNorm -> Linear: ~1e-2 on O(1) values
+        torch.testing.assert_close(out[i].float(), ref[i], atol=4e-2, rtol=3e-2)
+        assert float((out[i].float() - ref[i]).abs().mean()) < 6e-3
+
+
+def test_row_stats(lib):
+    torch.manual_seed(40)
+    m = 1003
+    x = [torch.randn(m, 512, device=DEV) * 2 - 0.3 for _ in range(2)]
+    xb = [torch.empty(m, 512, device=DEV, dtype=torch.bfloat16) for _ in range(2)]
+    st = [torch.full((m, _lib.LN_SLOTS, 2), float('nan'), device=DEV) for _ in range(2)]
+    a = _lib.RowStatsArgs()
+    a.x, a.out_bf16, a.ln_stats, a.groups, a.M = _lib.pair(*x), _lib.pair(*xb), _lib.pair(*st), 2, m
+    _lib.check(lib.some_row_stats(C.byref(a), stream()), 'some_row_stats')
+    torch.cuda.synchronize()
+    for i in range(2):
+        assert torch.equal(xb[i], x[i].to(torch.bfloat16))
+        torch.testing.assert_close(st[i][:, 0, 0], x[i].sum(1), atol=1e-3, rtol=1e-5)
+        torch.testing.assert_close(st[i][:, 0, 1], (x[i] * x[i]).sum(1), atol=1e-2, rtol=1e-5)
+
+
 @pytest.mark.parametrize('n,epi', [(128, 'sigmoid'), (129, 'softmax'), (128, 'logits'), (129, 'logits')])
 def test_gemm_heads(lib, n, epi):
     torch.manual_seed(4)

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), (declared ^ set(_lib.EXPORTS))
     for name in declared:
         assert hasattr(lib, name), f'{name} declared in include/some_b200.h but not exported'
-    assert lib.some_version() == 100
+    assert lib.some_version() == 200
     assert lib.some_last_error() is not None
 
 
@@ -37,7 +37,7 @@ def test_abi_struct_sizes_match_header_layout():
     """ctypes mirrors of the header structs: pointer arrays first, then ints (catches field drift)."""
     from some_b200 import _lib
     import ctypes as C
-    assert C.sizeof(_lib.GemmArgs) == 10 * 8 + 7 * 4 + 4
+    assert C.sizeof(_lib.GemmArgs) == 10 * 8 + 7 * 4 + 4 + 4 * 8 + 4 + 4 + 2 * 8   # + ln_s, ln_stats, ln_parts (+pad), out_bf16
     assert C.sizeof(_lib.LnArgs) == 10 * 8 + 2 * 4
     assert C.sizeof(_lib.AttnArgs) == 4 * 8 + 3 * 4 + 4 + 8 + 4 + 4  # incl. alignment / tail padding
     assert C.sizeof(_lib.DwconvArgs) == 8 * 8 + 2 * 4 + 8 + 4 + 4
@@ -51,10 +51,11 @@ def test_abi_struct_layouts_match_the_c_compiler(tmp_path):
     from some_b200 import _lib
     if shutil.which('gcc') is None:
         pytest.skip('gcc not available')
-    pairs = [('some_gemm_args', _lib.GemmArgs, 'alpha'), ('some_ln_args', _lib.LnArgs, 'M'),
+    pairs = [('some_gemm_args', _lib.GemmArgs, 'out_bf16'), ('some_ln_args', _lib.LnArgs, 'M'),
+             ('some_rowstats_args', _lib.RowStatsArgs, 'M'), ('some_profile_record', _lib.ProfileRecord, 'work'),
              ('some_attn_args', _lib.AttnArgs, 'max_frames'), ('some_dwconv_args', _lib.DwconvArgs, 'max_frames'),
-             ('some_decode_args', _lib.DecodeArgs, 'scratch'), ('some_block_weights', _lib.BlockWeightsC, 'b_pw2'),
-             ('some_model', _lib.ModelC, 'b_cut'), ('some_workspace', _lib.WorkspaceC, 'bounds')]
+             ('some_decode_args', _lib.DecodeArgs, 'scratch'), ('some_block_weights', _lib.BlockWeightsC, 'b_pw1f'),
+             ('some_model', _lib.ModelC, 'ln_fold'), ('some_workspace', _lib.WorkspaceC, 'ln_stats')]
     src = '#include <stdio.h>\n#include <stddef.h>\n#include "some_b200.h"\nint main(void){\n'
     for name, _, last in pairs:
         src += f'  printf("%zu %zu\\n", sizeof({name}), offsetof({name}, {last}));\n'
@@ -143,7 +144,7 @@ def test_bn_folding_and_packing_match_torch():
     cfg = synth.named_config('two_head', lay=1)
     sd = synth.fabricate_state_dict(cfg, seed=11)
     p = 'model.att1'
-    bw = weights.BlockWeights(sd, p, 'cpu')
+    bw = weights.BlockWeights(sd, p, 'cpu', weights.RoundingRegistry('cpu'))
     x = torch.randn(1, 512, 50)
     ref = torch.nn.functional.batch_norm(
         torch.nn.functional.conv1d(x, sd[p + '.conv.depthwise_conv.weight'], sd[p + '.conv.depthwise_conv.bias'],
@@ -169,9 +170,10 @@ def test_mel_tables_match_golden_basis(golden_dir):
     assert np.array_equal(dense, ref)
     assert torch.equal(t['window'], torch.hann_window(2048))
     tw = t['twiddle'].double()
-    assert tw.shape == (1392, 2)
-    assert abs(float(tw[384, 0])) < 1e-7 and abs(float(tw[384, 1]) + 1.0) < 1e-7    # stage 0, m = 2, j = 128: W_1024^256 = -i
-    assert abs(float(tw[1020 + 256, 0]) - np.cos(-2 * np.pi * 256 / 2048)) < 1e-7   # unpack table W_2048^k
+    assert tw.shape == (1396, 2)
+    assert abs(float(tw[16 * 32 + 16, 0])) < 1e-7 and abs(float(tw[16 * 32 + 16, 1]) + 1.0) < 1e-7   # W_1024^(16 * 16) = -i
+    assert abs(float(tw[3 * 32 + 5, 0]) - np.cos(-2 * np.pi * 15 / 1024)) < 1e-7       # [k1 = 3][n2 = 5]
+    assert abs(float(tw[1024 + 256, 0]) - np.cos(-2 * np.pi * 256 / 2048)) < 1e-7      # unpack table W_2048^k
 
 
 # --------------------------------------------------------------------------- sharding + gather

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out/c1
 O=gpurun_out/c1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/smi.txt 2>&1
-timeout 600 python -m pytest tests -m gpu -x -q > $O/pytest_base.log 2>&1; echo "pytest base rc=$?"; tail -3 $O/pytest_base.log
+timeout 900 python -m pytest tests -m gpu -x -q -s > $O/pytest_base.log 2>&1; echo "pytest base rc=$?"; tail -3 $O/pytest_base.log
 B="--steps 4 --warmup 3 --no-cpu-baseline"
 timeout 600 python bench.py $B > $O/bench_base.json 2> $O/bench_base.err; echo "bench base rc=$?"
 for v in v7 v7p3 v7p4; do
