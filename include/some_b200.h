@@ -65,6 +65,18 @@ int some_mel_logmel(const float* wave, const int64_t* clip_start, const int64_t*
                     const float* twiddle, const float* window, float* out_f32, uint16_t* out_bf16, float clamp,
                     cudaStream_t stream);
 
+/* ---- K-mel-keyshift: MelSpectrogram.forward with keyshift != 0 and / or speed != 1
+ * (modules/rmvpe/spec.py:38-72; caller preprocessing/me_binarizer.py:235-247): n_fft = win_length = round(2048 * 2^(keyshift /
+ * 12)), hop = round(512 * speed), F.pad(pad_left = win / 2 (0 when center=False), ...), periodic Hann of n_fft points,
+ * magnitudes of bins 0..371 scaled by mag_scale = 2048 / n_fft (spec.py:68), same filterbank and log(clamp).
+ *   cu_frames  int32 [B + 1], T_b = 1 + (L_b + pad_left + pad_right - n_fft) / hop (= 1 + L_b / hop when center=True)
+ *   twiddle    f32 [n_fft][2] = exp(-2 pi i m / n_fft), host-computed in double;  window f32 [n_fft] */
+int some_mel_logmel_keyshift(const float* wave, const int64_t* clip_start, const int64_t* clip_len,
+                             const int32_t* cu_frames, int B, int max_frames, int n_fft, int hop, int pad_left,
+                             float mag_scale, const int32_t* mel_start, const int32_t* mel_count,
+                             const float* mel_weights, const float* twiddle, const float* window, float* out_f32,
+                             uint16_t* out_bf16, float clamp, cudaStream_t stream);
+
 /* ---- K-ln: nn.LayerNorm(512), eps 1e-5 (Gconform.py:57-63 norm1..norm5) over rows of x f32 [M, 512].
  *   out_bf16: normalised rows as bf16 (A operand of the next GEMM) or NULL
  *   out_f32 : normalised rows as f32 (the residual stream after norm5) or NULL (may alias x)
@@ -307,6 +319,55 @@ int some_col_means(const uint16_t* a, int M, int K, int lda, const float* ln_sta
  * prof and calib may be NULL. */
 int some_forward(const some_model* model, const some_workspace* ws, int M, int B, const int32_t* cu_frames,
                  int max_frames, int head, some_profiler* prof, some_calibration* calib, cudaStream_t stream);
+
+/* ---- some_forward_f32: the same trunk with fp32 operands on the CUDA cores (no tensor cores, no bf16, exact expf-based
+ * activations): the VALIDATION mode behind the "within 1e-3 fp32" line of the contract.  The reference inference path is fp32
+ * (inference/me_infer.py:65-76; pl_trainer_precision only affects training).  ~100x slower than some_forward; a checker, not a
+ * fallback: the product path never calls it.  Weights are the checkpoint's own fp32 tensors in nn.Linear layout [N, K]
+ * (to_q | to_kv concatenated, pointwise convs squeezed, depthwise taps [31][512] with BatchNorm folded, GLU producers NOT
+ * row-packed: first half = out, second half = gate). */
+typedef struct {
+  const float* ln_g[5];
+  const float* ln_b[5];
+  const float* ffn_w1[2];
+  const float* ffn_b1[2];
+  const float* ffn_w2[2];
+  const float* ffn_b2[2];
+  const float* w_qkv;
+  const float* w_out;
+  const float* b_out;
+  const float* w_pw1;
+  const float* b_pw1;
+  const float* w_dw;
+  const float* b_dw;
+  const float* w_pw2;
+  const float* b_pw2;
+} some_block_weights_f32;
+typedef struct {
+  int lay, outdim;
+  const float* w_in[2];
+  const float* b_in[2];
+  const some_block_weights_f32* blocks; /* host array [(lay + 1) * 2], entry 2 i + s */
+  const float* const* glu_w;            /* host array [lay * 2]: 2 i + 0 = glu1 (fed by midi), 2 i + 1 = glu2 */
+  const float* const* glu_b;
+  const float* w_head;
+  const float* b_head;
+  const float* w_cut;
+  float b_cut;
+} some_model_f32;
+typedef struct {
+  float* x[2];         /* f32 [M,512] residual streams */
+  float* a[2];         /* f32 [M,512] */
+  float* h[2];         /* f32 [M,2048] */
+  float* qkv[2];       /* f32 [M,1536] */
+  float* g[2];         /* f32 [M,512] */
+  float* y[2];         /* f32 [M,1024] GLU pre-activations */
+  const float* units;  /* f32 [M,80] log-mel (input: some_mel_logmel out_f32) */
+  float* probs;        /* f32 [M,outdim] (output) */
+  float* bounds;       /* f32 [M] (output) */
+} some_workspace_f32;
+int some_forward_f32(const some_model_f32* model, const some_workspace_f32* ws, int M, int B, const int32_t* cu_frames,
+                     int max_frames, int head, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -8,6 +8,7 @@ TEST INFRASTRUCTURE — see oracle/__init__.py.
 """
 import functools
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -22,14 +23,24 @@ def _mel_basis(sr, n_fft, n_mels, fmin, fmax):
 
 # --------------------------------------------------------------------------- mel front end
 def log_mel(audio: torch.Tensor, sr=44100, n_fft=2048, hop=512, n_mels=80, fmin=40, fmax=8000,
-            clamp=1e-5) -> torch.Tensor:
-    """modules/rmvpe/spec.py:38-72 with keyshift=0, speed=1, center=True.
-    audio [B, L] float32 -> log-mel [B, n_mels, T], T = 1 + L // hop."""
-    win = torch.hann_window(n_fft)                                     # spec.py:44-46 (periodic Hann)
-    audio = F.pad(audio, (n_fft // 2, (n_fft + 1) // 2))              # spec.py:47-50 zero pad 1024/1024
-    fft = torch.stft(audio, n_fft=n_fft, hop_length=hop, win_length=n_fft, window=win,
-                     center=False, return_complex=True)               # spec.py:52-60
-    magnitude = fft.abs()                                             # spec.py:61
+            clamp=1e-5, keyshift=0, speed=1, center=True) -> torch.Tensor:
+    """modules/rmvpe/spec.py:38-72.  audio [B, L] float32 -> log-mel [B, n_mels, T]; with the defaults (the inference path)
+    T = 1 + L // hop.  keyshift / speed: the binarizer's augmentation path (spec.py:39-46,63-68)."""
+    factor = 2 ** (keyshift / 12)                                      # spec.py:39
+    n_fft_new = int(np.round(n_fft * factor))                          # :40 (win_length == n_fft in every shipped config)
+    hop_new = int(np.round(hop * speed))                               # :42
+    win = torch.hann_window(n_fft_new)                                 # :44-46 (periodic Hann)
+    if center:
+        audio = F.pad(audio, (n_fft_new // 2, (n_fft_new + 1) // 2))  # :47-50 zero pad
+    fft = torch.stft(audio, n_fft=n_fft_new, hop_length=hop_new, win_length=n_fft_new, window=win,
+                     center=False, return_complex=True)               # :52-60
+    magnitude = fft.abs()                                             # :61
+    if keyshift != 0:                                                  # :63-68
+        size = n_fft // 2 + 1
+        resize = magnitude.size(1)
+        if resize < size:
+            magnitude = F.pad(magnitude, (0, 0, 0, size - resize))
+        magnitude = magnitude[:, :size, :] * n_fft / n_fft_new
     basis = _mel_basis(sr, n_fft, n_mels, fmin, fmax)                 # spec.py:22-29 (built once)
     mel_output = torch.matmul(basis, magnitude)                       # spec.py:70
     return torch.log(torch.clamp(mel_output, min=clamp))              # spec.py:71

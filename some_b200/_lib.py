@@ -89,12 +89,31 @@ class WorkspaceC(C.Structure):
                 ('probs', _vp), ('bounds', _vp), ('xb', _vp * 2), ('ln_stats', _vp * 2)]
 
 
+class BlockWeightsF32C(C.Structure):
+    _fields_ = [('ln_g', _vp * 5), ('ln_b', _vp * 5), ('ffn_w1', _vp * 2), ('ffn_b1', _vp * 2), ('ffn_w2', _vp * 2),
+                ('ffn_b2', _vp * 2), ('w_qkv', _vp), ('w_out', _vp), ('b_out', _vp), ('w_pw1', _vp), ('b_pw1', _vp),
+                ('w_dw', _vp), ('b_dw', _vp), ('w_pw2', _vp), ('b_pw2', _vp)]
+
+
+class ModelF32C(C.Structure):
+    _fields_ = [('lay', C.c_int), ('outdim', C.c_int), ('w_in', _vp * 2), ('b_in', _vp * 2),
+                ('blocks', C.POINTER(BlockWeightsF32C)), ('glu_w', C.POINTER(_vp)), ('glu_b', C.POINTER(_vp)),
+                ('w_head', _vp), ('b_head', _vp), ('w_cut', _vp), ('b_cut', C.c_float)]
+
+
+class WorkspaceF32C(C.Structure):
+    _fields_ = [('x', _vp * 2), ('a', _vp * 2), ('h', _vp * 2), ('qkv', _vp * 2), ('g', _vp * 2), ('y', _vp * 2),
+                ('units', _vp), ('probs', _vp), ('bounds', _vp)]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     'some_version': (C.c_int, []),
     'some_last_error': (C.c_char_p, []),
     'some_mel_logmel': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   C.c_float, _vp]),
+    'some_mel_logmel_keyshift': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _vp, _vp,
+                                           _vp, _vp, _vp, _vp, _vp, C.c_float, _vp]),
     'some_layernorm': (C.c_int, [C.POINTER(LnArgs), _vp]),
     'some_gemm': (C.c_int, [C.POINTER(GemmArgs), _vp]),
     'some_attention_varlen': (C.c_int, [C.POINTER(AttnArgs), _vp]),
@@ -108,6 +127,8 @@ EXPORTS = {
     'some_col_means': (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp]),
     'some_forward': (C.c_int, [C.POINTER(ModelC), C.POINTER(WorkspaceC), C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp,
                                C.POINTER(CalibrationC), _vp]),
+    'some_forward_f32': (C.c_int, [C.POINTER(ModelF32C), C.POINTER(WorkspaceF32C), C.c_int, C.c_int, _vp, C.c_int, C.c_int,
+                                   _vp]),
     'some_profiler_create': (C.c_int, [C.c_int, C.POINTER(_vp)]),
     'some_profiler_destroy': (C.c_int, [_vp]),
     'some_profiler_reset': (C.c_int, [_vp]),

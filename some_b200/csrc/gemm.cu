@@ -510,11 +510,7 @@ struct PairCfg {
   static constexpr bool TMA_EPI = LNP || EPI == SOME_EPI_RESID_F32 || EPI == SOME_EPI_GLU_RESID_F32;
   static constexpr bool LNC = EPI == SOME_EPI_LN_STORE_BF16 || EPI == SOME_EPI_LN_SILU_BF16 || EPI == SOME_EPI_LN_GLU_BF16;
   static constexpr int BASE = LNC ? EPI - SOME_EPI_LN_STORE_BF16 : EPI;   // staged epilogues: STORE / SILU / GLU
-#ifdef SOME_GEMM_LNP_STAGES
-  static constexpr int STAGES = LNP ? SOME_GEMM_LNP_STAGES : 5;
-#else
   static constexpr int STAGES = LNP ? 4 : 5;
-#endif
   // per epilogue warp: one 32 x 128 B transposition tile, or two residual slabs (+ the bf16 tile of the LN producers)
   static constexpr int WARP_BYTES = TMA_EPI ? (LNP ? 12288 : 8192) : 4096;
   static constexpr int EPI_BYTES = EPI_WARPS * WARP_BYTES;
@@ -786,14 +782,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const GemmGroup& g = p.g[grp];
         const int row_base = m_blk * 2 * BLOCK_M + rank * BLOCK_M + quad * 32;
         if constexpr (Cfg::LNC) {
-          // The row statistics of the NEXT tile are pulled into L1 now: read at the start of that tile's epilogue they would
-          // cost a DRAM round trip with nothing to overlap it (measured: +25 % on the K = 512 consumer GEMMs).
+          // The row statistics of the NEXT tile are pulled into L2 now: read at the start of that tile's epilogue they would
+          // cost a DRAM round trip with nothing to overlap it.
           const int nt = tile + num_pairs;
           if (nt < num_tiles) {
             const int ng = nt / tiles_per_group;
             const int nrow = ((nt - ng * tiles_per_group) / num_n) * 2 * BLOCK_M + rank * BLOCK_M + quad * 32 + lane;
             if (nrow < p.M)
-              asm volatile("prefetch.global.L1 [%0];" ::"l"(p.g[ng].ln_stats + (size_t)nrow * SOME_LN_SLOTS * 2));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.g[ng].ln_stats + (size_t)nrow * SOME_LN_SLOTS * 2));
           }
         }
         mbar_wait(&tmem_full[acc], acc_phase);

@@ -4,11 +4,13 @@ libsome_b200.so in order on the current CUDA stream and unpacks the decoded note
 Equivalent to running the reference's batch-1 loop (inference/base_infer.py:46-53) once per clip:
 clips never interact (per-clip attention, per-clip zero-padded depthwise conv, per-clip decode).
 The trunk is sequenced natively (csrc/forward.cu: some_forward); per conform_blocke (Gconform.py:56-63), both streams
-(midi / bound) in every launch, norm1..norm4 folded into the GEMMs around them (SOME_B200_LN_FOLD=0 restores the
-stand-alone LayerNorm launches):
-    GEMM(ffn1.ln1')+SiLU -> GEMM(ffn1.ln2)*0.5+x -> GEMM(to_q|to_kv') -> attention -> GEMM(to_out)+x ->
-    GEMM(pointwise_conv1')+GLU -> dwconv+BN+SiLU -> GEMM(pointwise_conv2)+x -> GEMM(ffn2.ln1')+SiLU ->
-    GEMM(ffn2.ln2)*0.5+x -> LN5
+(midi / bound) in every launch:
+    LN1 -> GEMM(ffn1.ln1)+SiLU -> GEMM(ffn1.ln2)*0.5+x -> LN2 -> GEMM(to_q|to_kv) -> attention ->
+    GEMM(to_out)+x -> LN3 -> GEMM(pointwise_conv1)+GLU -> dwconv+BN+SiLU -> GEMM(pointwise_conv2)+x ->
+    LN4 -> GEMM(ffn2.ln1)+SiLU -> GEMM(ffn2.ln2)*0.5+x -> LN5
+SOME_B200_LN_FOLD=1 selects the variant with norm1..norm4 folded into the GEMMs around them (11 instead of 15 launches per
+block; measured 0.9 ms SLOWER per 64 x 30 s step on B200 because the K = 512 consumer GEMMs are epilogue-bound:
+profiles/r02_ln_fold.md), kept as a validated option.
 The residual stream x is fp32 [M, 512]; GEMM operands are bf16; accumulation is fp32.
 """
 from __future__ import annotations
@@ -38,8 +40,12 @@ def pinned_array(num_samples: int) -> np.ndarray:
 
 
 class _Workspace:
+    _count = 0
+
     def __init__(self, m: int, outdim: int, device):
         bf, f32 = torch.bfloat16, torch.float32
+        _Workspace._count += 1
+        self.serial = _Workspace._count       # never reused (CUDA-graph cache keys)
         self.m = m
         self.x = torch.empty((2, m, DIM), dtype=f32, device=device)          # residual streams
         self.a = torch.empty((2, m, DIM), dtype=bf, device=device)           # LN out / attention out / dwconv out
@@ -72,8 +78,10 @@ class Engine:
         if self.device.type != 'cuda':
             raise _lib.SomeB200Error('some_b200 runs on CUDA devices only (sm_100a); there is no CPU path')
         self.quantized = False
+        self._state_dict = state_dict        # fp32 masters for the validation path (infer_accurate), built lazily
+        self._f32 = None
         self.w = ModelWeights(state_dict, config, self.device)
-        self.ln_fold = os.environ.get('SOME_B200_LN_FOLD', '1') != '0'
+        self.ln_fold = os.environ.get('SOME_B200_LN_FOLD', '0') != '0'
         self._cmodel, self._cmodel_keep = build_c_model(self.w, self.ln_fold)
         self.mel = mel_tables(config, self.device)
         self.outdim = config['midi_num_bins']
@@ -88,6 +96,9 @@ class Engine:
         # (some_profiler), the kernels launched from here (mel, decode) are bracketed by _mark()
         self.prof: Optional[dict] = None
         self._cprof = None
+        self._graphs: dict = {}
+        self._graph_seen: dict = {}
+        self.use_graphs = os.environ.get('SOME_B200_GRAPHS', '1') != '0'
         self._corrected: set = set()
         self.bias_correction = os.environ.get('SOME_B200_BIAS_CORRECTION', '1') != '0'
         if self.bias_correction:
@@ -318,6 +329,36 @@ class Engine:
     # the split is geometric: a small first chunk gets the GPU going, the later ones stay big.
     CHUNK_FRACTIONS = (0.125, 0.375, 0.5)
     MIN_CHUNK_FRAMES = 16384
+    GRAPH_MAX_FRAMES = 12288      # chunks up to this many frames go through CUDA-graph replay (SOME_B200_GRAPHS=0 disables)
+
+    def _graphed(self, key, fn):
+        """Runs ``fn`` (kernel launches on the current stream, no allocation, no sync) through a cached CUDA graph: eager the
+        first time a key is seen (function attributes / tensor maps get set up, one-off shapes are never captured), captured
+        on the second, replayed from then on.  At most 32 graphs are kept."""
+        seen = self._graph_seen.get(key, 0)
+        self._graph_seen[key] = seen + 1
+        g = self._graphs.get(key)
+        if g is None:
+            if seen == 0 or len(self._graphs) >= 32:
+                if len(self._graph_seen) > 4096:
+                    self._graph_seen.clear()
+                fn()
+                return
+            launches0 = self.launches
+            stream = torch.cuda.current_stream(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self._graph_stream(stream)):
+                fn()
+            self._graphs[key] = (g, self.launches - launches0)
+            self.launches = launches0
+            g = self._graphs[key]
+        g[0].replay()
+        self.launches += g[1]
+
+    def _graph_stream(self, stream):
+        if getattr(self, '_gstream', None) is None:
+            self._gstream = torch.cuda.Stream(self.device)
+        return self._gstream
 
     def _chunks(self, cu: np.ndarray) -> List[tuple]:
         b, m = len(cu) - 1, int(cu[-1])
@@ -463,9 +504,18 @@ class Engine:
             note_midi = o[4 * bc + 4 * mc:4 * bc + 8 * mc].view(torch.float32)
             note_rest = o[4 * bc + 8 * mc:]
             mel_f32 = torch.empty((mc, 80), dtype=torch.float32, device=dev) if return_intermediates else None
-            self.run_mel(wave_d[lo:], tab_dev[:bc], tab_dev[bc:2 * bc], cu_d, bc, max_frames, mel_f32, ws.units)
-            self.run_trunk(ws, mc, bc, cu_d, max_frames, 'softmax' if quantized else 'sigmoid')
-            self.run_decode(ws, mc, bc, cu_d, note_count, quantized, out=(note_midi, note_dur, note_rest))
+            def launch_chunk():
+                self.run_mel(wave_d[lo:], tab_dev[:bc], tab_dev[bc:2 * bc], cu_d, bc, max_frames, mel_f32, ws.units)
+                self.run_trunk(ws, mc, bc, cu_d, max_frames, 'softmax' if quantized else 'sigmoid')
+                self.run_decode(ws, mc, bc, cu_d, note_count, quantized, out=(note_midi, note_dur, note_rest))
+
+            if mc <= self.GRAPH_MAX_FRAMES and self.use_graphs and self.prof is None and not return_intermediates:
+                # small batches are launch-bound (~56 launches of a few microseconds each): replay them as ONE CUDA graph,
+                # keyed by everything the captured kernel arguments depend on
+                self._graphed((wave_d.data_ptr() + 4 * lo, tab_dev.data_ptr(), cu_d.data_ptr(), o.data_ptr(), ws.serial, bc, mc,
+                               max_frames, bool(quantized), self.ln_fold), launch_chunk)
+            else:
+                launch_chunk()
             if return_intermediates:
                 extra = (mel_f32, ws.probs[:mc], ws.bounds[:mc])
         self._h2d_done = ev if layout else None
@@ -561,6 +611,44 @@ class Engine:
                 extra = tuple(t.cpu() for t in extra)
             torch.cuda.current_stream(dev).synchronize()
             return self.unpack_slab(out_h[:slab.numel()].numpy(), cu, layout, extra)
+
+    def infer_accurate(self, waveforms: Sequence[np.ndarray], quantized: bool = False) -> List[Dict[str, np.ndarray]]:
+        """VALIDATION mode: the same waveform -> notes path with the trunk in fp32 on the CUDA cores (some_forward_f32,
+        csrc/accurate.cu) — no bf16, no tensor cores, exact activations.  Asserts the "within 1e-3 fp32" line of the contract
+        (tests/test_gpu_accurate.py) and shows that operand rounding is the only source of note differences in the product
+        path.  ~100x slower than infer(); one clip at a time; returns mel / probs / bounds with the notes."""
+        from .weights import build_f32_model
+        dev = self.device
+        out = []
+        with torch.cuda.device(dev):
+            if self._f32 is None:
+                self._f32 = build_f32_model(self._state_dict, self.config, dev)
+            cmodel = self._f32[0]
+            head = _lib.EPI_SOFTMAX_F32 if quantized else _lib.EPI_SIGMOID_F32
+            for w in waveforms:
+                host, tables, cu = self.pack([w])
+                m = int(cu[-1])
+                wave_d, tab_d, cu_d = host.to(dev), tables.to(dev), torch.from_numpy(cu).to(dev)
+                f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+                t = {'x': f(2, m, DIM), 'a': f(2, m, DIM), 'h': f(2, m, FFN_DIM), 'qkv': f(2, m, 3 * DIM), 'g': f(2, m, DIM),
+                     'y': f(2, m, 2 * DIM), 'units': f(m, 80), 'probs': f(m, self.outdim), 'bounds': f(m)}
+                c = _lib.WorkspaceF32C()
+                for s in range(2):
+                    for k in ('x', 'a', 'h', 'qkv', 'g', 'y'):
+                        getattr(c, k)[s] = t[k][s].data_ptr()
+                c.units, c.probs, c.bounds = t['units'].data_ptr(), t['probs'].data_ptr(), t['bounds'].data_ptr()
+                self.run_mel(wave_d, tab_d[:1], tab_d[1:], cu_d, 1, m, t['units'], None)
+                _lib.check(self.lib.some_forward_f32(C.byref(cmodel), C.byref(c), m, 1, cu_d.data_ptr(), m, head, self._stream),
+                           'some_forward_f32')
+                ws = self.workspace(m)
+                nc = torch.empty(1, dtype=torch.int32, device=dev)
+                self.run_decode(ws, m, 1, cu_d, nc, quantized, probs=t['probs'], bounds=t['bounds'])
+                n = int(nc.item())
+                out.append({'note_midi': ws.note_midi[:n].cpu().numpy(),
+                            'note_dur': ws.note_dur[:n].cpu().numpy().astype(np.int64) * self.timestep,
+                            'note_rest': ws.note_rest[:n].cpu().numpy().astype(bool),
+                            'mel': t['units'].cpu().numpy(), 'probs': t['probs'].cpu().numpy(), 'bounds': t['bounds'].cpu().numpy()})
+        return out
 
     def unpack(self, cu, nc, nm, nd, nr, extra=None) -> List[Dict[str, np.ndarray]]:
         dur_s = nd * self.timestep     # me_infer.py:95: int64 * python float -> float64; int32 * float gives the same float64s

@@ -233,3 +233,51 @@ def build_c_model(w: ModelWeights, ln_fold: bool = True):
     m.w_head, m.b_head, m.w_cut, m.b_cut = w.w_head.data_ptr(), w.b_head.data_ptr(), w.w_cut.data_ptr(), w.b_cut
     m.ln_fold = int(bool(ln_fold))
     return m, (blocks, glu_w, glu_b)
+
+
+def build_f32_model(sd, config: dict, device):
+    """fp32 weights of the validation path (some_forward_f32, csrc/accurate.cu): the checkpoint's own tensors in nn.Linear
+    layout, to_q | to_kv concatenated, BatchNorm folded into the depthwise taps (in double), nothing rounded or packed.
+    Returns (ModelF32C, keepalive)."""
+    import ctypes as C
+    f32 = lambda t: t.to(device=device, dtype=torch.float32).contiguous()
+    keep = []
+
+    def ptr(t):
+        t = f32(t)
+        keep.append(t)
+        return t.data_ptr()
+
+    lay, outdim = config['midi_extractor_args']['lay'], config['midi_num_bins']
+    prefixes = [f'model.cf_lay.{i}.att{s}' for i in range(lay) for s in (1, 2)] + ['model.att1', 'model.att2']
+    blocks = (_lib.BlockWeightsF32C * len(prefixes))()
+    for b, p in zip(blocks, prefixes):
+        for k in range(5):
+            b.ln_g[k], b.ln_b[k] = ptr(sd[f'{p}.norm{k + 1}.weight']), ptr(sd[f'{p}.norm{k + 1}.bias'])
+        for k, name in enumerate(('ffn1', 'ffn2')):
+            b.ffn_w1[k], b.ffn_b1[k] = ptr(sd[f'{p}.{name}.ln1.weight']), ptr(sd[f'{p}.{name}.ln1.bias'])
+            b.ffn_w2[k], b.ffn_b2[k] = ptr(sd[f'{p}.{name}.ln2.weight']), ptr(sd[f'{p}.{name}.ln2.bias'])
+        b.w_qkv = ptr(torch.cat([sd[f'{p}.att.to_q.weight'], sd[f'{p}.att.to_kv.weight']], dim=0))
+        b.w_out, b.b_out = ptr(sd[f'{p}.att.to_out.0.weight']), ptr(sd[f'{p}.att.to_out.0.bias'])
+        b.w_pw1, b.b_pw1 = ptr(sd[f'{p}.conv.pointwise_conv1.weight'][:, :, 0]), ptr(sd[f'{p}.conv.pointwise_conv1.bias'])
+        scale = sd[f'{p}.conv.norm.weight'].double() / torch.sqrt(sd[f'{p}.conv.norm.running_var'].double() + BN_EPS)
+        dw = sd[f'{p}.conv.depthwise_conv.weight'][:, 0, :].double()
+        b.w_dw = ptr((dw * scale[:, None]).t())
+        b.b_dw = ptr((sd[f'{p}.conv.depthwise_conv.bias'].double() - sd[f'{p}.conv.norm.running_mean'].double()) * scale
+                     + sd[f'{p}.conv.norm.bias'].double())
+        b.w_pw2, b.b_pw2 = ptr(sd[f'{p}.conv.pointwise_conv2.weight'][:, :, 0]), ptr(sd[f'{p}.conv.pointwise_conv2.bias'])
+    n_glu = max(2 * lay, 1)
+    glu_w, glu_b = (C.c_void_p * n_glu)(), (C.c_void_p * n_glu)()
+    for i in range(lay):
+        for s in range(2):
+            glu_w[2 * i + s] = ptr(sd[f'model.cf_lay.{i}.glu{s + 1}.0.weight'])
+            glu_b[2 * i + s] = ptr(sd[f'model.cf_lay.{i}.glu{s + 1}.0.bias'])
+    m = _lib.ModelF32C()
+    m.lay, m.outdim = lay, outdim
+    m.w_in[0], m.w_in[1] = ptr(sd['model.inln.weight']), ptr(sd['model.inln1.weight'])
+    m.b_in[0], m.b_in[1] = ptr(sd['model.inln.bias']), ptr(sd['model.inln1.bias'])
+    m.blocks = C.cast(blocks, C.POINTER(_lib.BlockWeightsF32C))
+    m.glu_w, m.glu_b = C.cast(glu_w, C.POINTER(C.c_void_p)), C.cast(glu_b, C.POINTER(C.c_void_p))
+    m.w_head, m.b_head = ptr(sd['model.outln.weight']), ptr(sd['model.outln.bias'])
+    m.w_cut, m.b_cut = ptr(sd['model.cutheard.weight'][0]), float(sd['model.cutheard.bias'][0])
+    return m, (keep, blocks, glu_w, glu_b)

@@ -484,3 +484,30 @@ def test_decode_quantized_matches_reference_exactly(lib, golden_dir):
         np.testing.assert_array_equal(got_midi, g[f'q{i}_note_midi'])
         np.testing.assert_array_equal(got_dur.astype(np.int64) * (512 / 44100), g[f'q{i}_note_dur'])
         np.testing.assert_array_equal(got_rest, g[f'q{i}_note_rest'])
+
+
+def test_keyshift_mel_matches_reference_golden(golden_dir):
+    """some_b200.spec.MelSpectrogram (drop-in for modules/rmvpe/spec.py) on the key-shift / speed / center=False paths
+    (direct-DFT kernel some_mel_logmel_keyshift) against the outputs of the unmodified reference (tests/golden/keyshift.npz);
+    keyshift = 0 goes through the fused FFT kernel."""
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    from some_b200 import synth
+    from some_b200.spec import MelSpectrogram
+    g = np.load(golden_dir / 'keyshift.npz')
+    audio = torch.from_numpy(synth.synth_waveform(int(g['seed']), seconds=float(g['seconds']))).to(DEV)
+    mel = MelSpectrogram(80, 44100, 2048, 512, mel_fmin=40, mel_fmax=8000)
+    assert np.array_equal(mel.mel_basis.numpy(), np.load(golden_dir / 'mel.npz')['mel_basis'])
+    cases = [(f'ks_{k}', dict(keyshift=k)) for k in range(-5, 6)]
+    cases += [('ks_frac_2.37', dict(keyshift=2.37)), ('speed_1.25', dict(speed=1.25)), ('nocenter_ks3', dict(keyshift=3, center=False))]
+    for key, kw in cases:
+        got = mel(audio.unsqueeze(0), **kw)[0].cpu().numpy()
+        assert got.shape == g[key].shape, (key, got.shape, g[key].shape)
+        # fp32 DFT over <= 2734 terms against torch's FFT; log() amplifies relative errors of near-clamp bands
+        err = float(np.abs(got - g[key]).max())
+        assert err < 1e-3, (key, err)
+    # batched call == per-clip calls
+    two = torch.stack([audio, audio.flip(0)])
+    b = mel(two, keyshift=-3)
+    assert torch.equal(b[0], mel(audio.unsqueeze(0), keyshift=-3)[0])
+    assert torch.equal(b[1], mel(audio.flip(0).unsqueeze(0), keyshift=-3)[0])

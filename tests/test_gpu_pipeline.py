@@ -92,8 +92,8 @@ def test_batched_equals_per_clip(tmp_path):
 
 
 def test_ln_fold_matches_standalone_layernorm(tmp_path):
-    """some_forward with norm1..norm4 folded into the GEMMs (product default) against the same sequencer with stand-alone
-    LayerNorm launches: same function up to bf16 operand rounding (bf16(x) . W*gamma vs bf16(LN(x)) . W), and the native
+    """some_forward with norm1..norm4 folded into the GEMMs (SOME_B200_LN_FOLD=1) against the same sequencer with stand-alone
+    LayerNorm launches (the product default): same function up to bf16 operand rounding (bf16(x) . W*gamma vs bf16(LN(x)) . W), and the native
     profiler sees the expected launch counts (15 + 12 lay folded, 18 + 16 lay unfolded)."""
     ins, _ = _plugin('two_head', tmp_path)
     eng = ins.model
@@ -116,7 +116,7 @@ def test_ln_fold_matches_standalone_layernorm(tmp_path):
         assert launches[fold] == eng.trunk_launches
         out[fold] = (ws.probs[:m].clone(), ws.bounds[:m].clone())
         assert not torch.isnan(out[fold][0]).any() and not torch.isnan(out[fold][1]).any()
-    eng.set_ln_fold(True)
+    eng.set_ln_fold(False)                     # the product default (the folded variant measured slower: profiles/r02_ln_fold.md)
     lay = eng.w.lay
     assert launches[True] == 15 + 12 * lay and launches[False] == 18 + 16 * lay
     # two bf16 evaluations of the same fp32 function: each is within ~2.5e-3 of it (tests/test_gpu_parity_long.py)

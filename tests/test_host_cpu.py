@@ -55,7 +55,9 @@ def test_abi_struct_layouts_match_the_c_compiler(tmp_path):
              ('some_rowstats_args', _lib.RowStatsArgs, 'M'), ('some_profile_record', _lib.ProfileRecord, 'work'),
              ('some_attn_args', _lib.AttnArgs, 'max_frames'), ('some_dwconv_args', _lib.DwconvArgs, 'max_frames'),
              ('some_decode_args', _lib.DecodeArgs, 'scratch'), ('some_block_weights', _lib.BlockWeightsC, 'b_pw1f'),
-             ('some_model', _lib.ModelC, 'ln_fold'), ('some_workspace', _lib.WorkspaceC, 'ln_stats')]
+             ('some_model', _lib.ModelC, 'ln_fold'), ('some_workspace', _lib.WorkspaceC, 'ln_stats'),
+             ('some_block_weights_f32', _lib.BlockWeightsF32C, 'b_pw2'), ('some_model_f32', _lib.ModelF32C, 'b_cut'),
+             ('some_workspace_f32', _lib.WorkspaceF32C, 'bounds'), ('some_calibration', _lib.CalibrationC, 'k')]
     src = '#include <stdio.h>\n#include <stddef.h>\n#include "some_b200.h"\nint main(void){\n'
     for name, _, last in pairs:
         src += f'  printf("%zu %zu\\n", sizeof({name}), offsetof({name}, {last}));\n'

@@ -174,3 +174,19 @@ def test_quantised_decode_matches_reference(golden_dir):
             np.testing.assert_array_equal(nm, g[f'q{i}_note_midi'])
             np.testing.assert_array_equal(nd * (512 / 44100), g[f'q{i}_note_dur'])
             np.testing.assert_array_equal(~nk, g[f'q{i}_note_rest'])
+
+
+def test_oracle_keyshift_mel_matches_reference(golden_dir):
+    """oracle.model.log_mel with keyshift / speed / center (modules/rmvpe/spec.py:39-46,63-68) against the unmodified
+    reference MelSpectrogram (tests/golden/make_golden_keyshift.py)."""
+    import torch
+    from oracle import model as omodel
+    from some_b200 import synth
+    g = np.load(golden_dir / 'keyshift.npz')
+    audio = torch.from_numpy(synth.synth_waveform(int(g['seed']), seconds=float(g['seconds']))).unsqueeze(0)
+    cases = [(f'ks_{k}', dict(keyshift=k)) for k in range(-5, 6)]
+    cases += [('ks_frac_2.37', dict(keyshift=2.37)), ('speed_1.25', dict(speed=1.25)), ('nocenter_ks3', dict(keyshift=3, center=False))]
+    for key, kw in cases:
+        got = omodel.log_mel(audio, fmin=40, fmax=8000, **kw)[0].numpy()
+        assert got.shape == g[key].shape, key
+        assert float(np.abs(got - g[key]).max()) < 2e-5, key        # same torch.stft; summation-order noise only
