@@ -157,8 +157,6 @@ typedef struct {
   int max_frames;           /* max_b T_b: grid = ceil(max_frames / 128) query tiles per clip */
 } some_attn_args;
 int some_attention_varlen(const some_attn_args* args, cudaStream_t stream);
-/* Same contract on the legacy mma.sync (HMMA) path; kept only as a cross-check for the tcgen05 kernel in tests. */
-int some_attention_varlen_mma(const some_attn_args* args, cudaStream_t stream);
 
 /* ---- K-dwconv: depthwise Conv1d(k=31, pad 15, groups=512) + BatchNorm1d(eval) + SiLU
  * (base_conv.py:66-68) on the packed [M, 512] bf16 layout (no transposes), zero halo per clip.

@@ -117,7 +117,6 @@ EXPORTS = {
     'some_layernorm': (C.c_int, [C.POINTER(LnArgs), _vp]),
     'some_gemm': (C.c_int, [C.POINTER(GemmArgs), _vp]),
     'some_attention_varlen': (C.c_int, [C.POINTER(AttnArgs), _vp]),
-    'some_attention_varlen_mma': (C.c_int, [C.POINTER(AttnArgs), _vp]),
     'some_dwconv_bn_silu': (C.c_int, [C.POINTER(DwconvArgs), _vp]),
     'some_bound_head': (C.c_int, [_vp, _vp, _vp, _vp, C.c_float, C.c_int, _vp, _vp]),
     'some_decode_scratch_bytes': (C.c_uint64, [C.c_int]),

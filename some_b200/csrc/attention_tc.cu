@@ -147,6 +147,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
+#ifdef SOME_ATTN_DIAG_NOMMA
+  if (warp < 2) {
+  } else
+#endif
   if (warp == 0) {
     if (elect_one_sync()) {
       mbar_arrive_expect_tx(q_full, TC_QTILE);
@@ -201,16 +205,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j % TC_STAGES;
         if (j + 2 < n_tiles) wait_kv(j + 2);      // off the critical path: before the p_full wait
+        ATTN_TRACE(2, j, 0);
         mbar_wait(&p_full[j & 1], (j >> 1) & 1);  // P_j in tensor memory (and O rescaled if it had to be)
         tc_fence_after_sync();
+        ATTN_TRACE(2, j, 1);
         const uint64_t vdesc = umma_desc_mnmajor_sw128(smem_u32(sKV + s * 2 * TC_KTILE + TC_KTILE), 1024);
         const uint32_t p_tmem = tmem_base + (j & 1) * TC_BN;  // P_j (bf16, two keys per column) overwrote S_j's first 32 columns
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // 16 keys per MMA: A +8 TMEM columns, B +16 key rows = 2 KB (+128)
           umma_bf16_ts(tmem_base + TC_O_COL + (j & 1) * 64, p_tmem + 8 * k, vdesc + 128 * k, idesc_pv, j >= 2 || k != 0);
+        ATTN_TRACE(2, j, 2);
         // S[j & 1] has been consumed (p_full_j): refill it two tiles ahead, right behind PV_j on the in-order tensor pipe
         if (j + 2 < n_tiles) issue_qk(j + 2);
         umma_commit(&kv_empty[s]);
+        ATTN_TRACE(2, j, 3);
       }
       umma_commit(all_done);
     }
@@ -225,46 +233,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
     const float c = 0.125f * 1.4426950408889634f;  // dim_head^-0.5 * log2(e)
     const uint64_t c2 = f2_pack(c, c);
     float m_used = -INFINITY, l = 0.f;
-    // SOME_ATTN_STALE_MAX: full tiles after the first are exponentiated against the STALE running maximum while their own
-    // maximum is gathered in the same pass (no separate max pass, one TMEM read of S instead of two); the maximum is brought
-    // up to date AFTER the tile (l at once, O at the start of the group's next tile, when PV of this one has retired).  The
-    // scale of P only has to stay far from overflow: a tile whose scores exceed the stale maximum by more than 2^64 is redone
-    // the exact way (never seen; the guard keeps the kernel correct for adversarial inputs).
-#ifdef SOME_ATTN_STALE_MAX
-    constexpr bool kStale = true;
-#else
-    constexpr bool kStale = false;
-#endif
-    bool pend = false;          // warp-uniform: an O rescale by pend_alpha is owed
-    float pend_alpha = 1.f;
-    auto rescale_o = [&](float alpha) {   // O[g] rows of this warp *= alpha (O must be quiescent)
-      uint32_t o[32];
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        tmem_ld_32x32(t_o + 32 * h, o);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-        tmem_st_32x32(t_o + 32 * h, o);
-      }
-      tmem_st_wait();
-    };
     int it = 0;
     for (int j = g; j < n_tiles; j += 2, ++it) {
       const int valid = min(TC_BN, T - j * TC_BN);  // keys of this tile inside the clip
+#ifndef SOME_ATTN_DIAG_NOMMA     // timing experiment only (wrong results): softmax warps free-running, no MMA / TMA
       mbar_wait(&s_full[g], it & 1);  // also: PV_{j-2} (this group's previous tile) has retired, O[g] is quiescent
+#endif
       tc_fence_after_sync();
-      ATTN_TRACE(g, j, 0);
-      if (pend) {
-        rescale_o(pend_alpha);
-        pend = false;
+#ifdef SOME_ATTN_DIAG_NOSOFTMAX  // timing experiment only (wrong results): hand-off chain and tensor work alone
+      if (true) {
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g]);
+        continue;
       }
-      bool exact = !kStale || it == 0 || valid != TC_BN;
-    redo_exact:
+#endif
+      ATTN_TRACE(g, j, 0);
       uint32_t v[32];
       // ---- pass 1: row maximum (the scores are re-read from tensor memory in pass 2: 32 live registers, not 64)
       float mx = -INFINITY;
-      if (exact) {
+      {
         uint32_t u[32];
         tmem_ld_32x32(t_s, v);  // both halves in flight before the single wait
         tmem_ld_32x32(t_s + 32, u);
@@ -294,15 +282,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
       }
       ATTN_TRACE(g, j, 1);
       // ---- lazy rescale decision (warp-uniform)
-      if (exact) {
-        const float m_new = fmaxf(m_used, mx);
-        const bool grow = (it == 0) || ((m_new - m_used) * c > 8.0f);
-        const bool do_rescale = __any_sync(0xffffffffu, grow);
-        if (do_rescale) {
-          const float alpha = (it == 0) ? 0.f : ex2_approx((m_used - m_new) * c);
-          m_used = m_new;
-          l *= alpha;
-          if (it > 0) rescale_o(alpha);  // O[g] *= alpha, only when a maximum of this warp moved (rare)
+      const float m_new = fmaxf(m_used, mx);
+      const bool grow = (it == 0) || ((m_new - m_used) * c > 8.0f);
+      const bool do_rescale = __any_sync(0xffffffffu, grow);
+      if (do_rescale) {
+        const float alpha = (it == 0) ? 0.f : ex2_approx((m_used - m_new) * c);
+        m_used = m_new;
+        l *= alpha;
+        if (it > 0) {  // O[g] *= alpha, only when a maximum of this warp moved (rare)
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            tmem_ld_32x32(t_o + 32 * h, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32(t_o + 32 * h, v);
+          }
+          tmem_st_wait();
         }
       }
       const float mc = m_used * c;
@@ -310,7 +306,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
       // ---- pass 2: p = 2^(s c - m c), row sum, bf16 pack
       uint32_t pk[32];
       uint64_t rs_a = f2_pack(0.f, 0.f), rs_b = rs_a;
-      float mq0 = -INFINITY, mq1 = -INFINITY;   // stale-max path: this tile's own maximum, gathered during the exp pass
       // 16-column quarters, software-pipelined: the tcgen05.ld of quarter q + 1 is in flight while quarter q is exponentiated
       auto quarter = [&](const uint32_t(&x)[16], int q) {
         if (valid == TC_BN) {
@@ -318,10 +313,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
           for (int i = 0; i < 16; i += 4) {
             const uint64_t ya = f2_fma(f2_pack(__uint_as_float(x[i]), __uint_as_float(x[i + 1])), c2, nmc2);
             const uint64_t yb = f2_fma(f2_pack(__uint_as_float(x[i + 2]), __uint_as_float(x[i + 3])), c2, nmc2);
-            if (kStale) {
-              mq0 = fmaxf(mq0, fmaxf(__uint_as_float(x[i]), __uint_as_float(x[i + 1])));
-              mq1 = fmaxf(mq1, fmaxf(__uint_as_float(x[i + 2]), __uint_as_float(x[i + 3])));
-            }
             float p0, p1, p2, p3;
             {
               float y0, y1;
@@ -369,25 +360,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
         tmem_ld_wait();
         quarter(xb, 3);
       }
-      if (!exact) {
-        const float mt = fmaxf(mq0, mq1);
-        if (__any_sync(0xffffffffu, (mt - m_used) * c > 64.0f)) {   // far beyond the stale maximum: redo this tile exactly
-          exact = true;
-          goto redo_exact;
-        }
-        const float m_new = fmaxf(m_used, mt);
-        if (__any_sync(0xffffffffu, (m_new - m_used) * c > 8.0f)) {
-          pend = true;
-          pend_alpha = ex2_approx((m_used - m_new) * c);
-          m_used = m_new;                      // l (below) and O (next tile / epilogue) follow
-        }
-      }
       {
         float s0, s1, s2, s3;
         f2_unpack(rs_a, s0, s1);
         f2_unpack(rs_b, s2, s3);
         l += (s0 + s1) + (s2 + s3);
-        if (pend) l *= pend_alpha;
       }
       // ---- P -> TMEM: bf16 pairs into the first 32 columns of this row's S buffer (all 64 scores have been consumed); the
       //      PV MMA takes its A operand straight from tensor memory, so P never touches shared memory.  QK_{j+2} overwrites
@@ -397,19 +374,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
       tmem_st_wait();
       tc_fence_before_sync();
       __syncwarp();
+#ifndef SOME_ATTN_DIAG_NOMMA
       if (lane == 0) mbar_arrive(&p_full[g]);
+#endif
       ATTN_TRACE(g, j, 3);
     }
     // ---- merge the two groups and write O / l -> bf16 -> out[row, head * 64 ..]; group g writes channels [32 g, 32 g + 32)
     stats[g * TC_BM + r] = make_float2(m_used, l);
+#ifndef SOME_ATTN_DIAG_NOMMA
     mbar_wait(all_done, 0);
+#endif
     tc_fence_after_sync();
-    if (pend) {
-      rescale_o(pend_alpha);
-      tc_fence_before_sync();
-    }
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    tc_fence_after_sync();
     const float2 sa = stats[r], sb = stats[TC_BM + r];
     const bool two = n_tiles > 1;
     const float m = fmaxf(sa.x, sb.x);

@@ -341,16 +341,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
 // fully coalesced 128-byte rows: lane -> (row = 4 it + lane / 8, 16-byte chunk = lane % 8).
 __device__ __forceinline__ uint32_t stage_off(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
-__device__ __forceinline__ void stage_flush(const GemmParams& p, const GemmGroup& g, int row_base, int lane,
-                                            const uint8_t* stage, size_t col_byte) {
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int row = it * 4 + (lane >> 3), ch = lane & 7;
-    const float4 v = *reinterpret_cast<const float4*>(stage + stage_off(row, ch));
-    if (row_base + row < p.M)
-      *reinterpret_cast<float4*>(static_cast<uint8_t*>(g.out) + (size_t)(row_base + row) * p.ld_out * 2 + col_byte + ch * 16) = v;
+// Hands one staged 32-row x 128-byte tile (bf16 outputs, 128-byte swizzle = the layout stage_off() writes) to a TMA store.
+// Two tiles per warp alternate, so the only wait is for the store issued two flushes ago (lane 0 owns the bulk groups).
+struct StageRing {
+  uint8_t* base;            // two 4 KB tiles of this warp
+  const CUtensorMap* map;   // bf16 output of the current group, box 32 rows x 64 columns
+  uint32_t count;           // flushes so far (across tiles)
+  __device__ __forceinline__ uint8_t* tile() const { return base + (count & 1) * 4096; }
+  // call before the first write into tile(): the store that last read it has finished reading shared memory
+  __device__ __forceinline__ void acquire(int lane) {
+    if (lane == 0) bulk_wait_group_read<1>();
+    __syncwarp();
   }
-}
+  __device__ __forceinline__ void flush(int lane, int col, int row_base) {
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(map, tile(), col, row_base);
+      bulk_commit_group();
+    }
+    ++count;
+  }
+};
 __device__ __forceinline__ void add_bias32(const float* bias, int col, float (&v)[32]) {
   if (bias == nullptr) return;
   const float4* b4 = reinterpret_cast<const float4*>(bias + col);
@@ -368,17 +380,17 @@ __device__ __forceinline__ uint64_t u2_pair(uint32_t lo, uint32_t hi) {   // two
 // was taken over bf16(x) and W' = W * gamma, so   LN(x) . W^T + bias = rstd * (acc - mean * s_n) + bias'_n   with
 // s_n = sum_k W'[n,k] (ln_s) and bias' = bias + W . beta (passed as bias).  ra2 = (rstd, rstd), nmu2 = (-mean, -mean) of
 // THIS thread's row.  Everything on the packed f32x2 pipes: 2 FFMA2 per pair (the plain bias add is 1 FADD2).
-template <bool kLn>
-__device__ __forceinline__ void bias_or_ln32(const GemmGroup& g, int col, const uint32_t (&acc)[32], uint64_t (&v)[16],
+template <bool kLn, int NC = 32>
+__device__ __forceinline__ void bias_or_ln32(const GemmGroup& g, int col, const uint32_t (&acc)[NC], uint64_t (&v)[NC / 2],
                                              uint64_t ra2, uint64_t nmu2) {
   if constexpr (!kLn) {
     if (g.bias == nullptr) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = u2_pair(acc[2 * i], acc[2 * i + 1]);
+      for (int i = 0; i < NC / 2; ++i) v[i] = u2_pair(acc[2 * i], acc[2 * i + 1]);
     } else {
       const float4* b4 = reinterpret_cast<const float4*>(g.bias + col);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < NC / 4; ++i) {
         const float4 b = __ldg(b4 + i);
         v[2 * i] = f2_add(u2_pair(acc[4 * i], acc[4 * i + 1]), f2_pack(b.x, b.y));
         v[2 * i + 1] = f2_add(u2_pair(acc[4 * i + 2], acc[4 * i + 3]), f2_pack(b.z, b.w));
@@ -388,7 +400,7 @@ __device__ __forceinline__ void bias_or_ln32(const GemmGroup& g, int col, const 
     const float4* b4 = reinterpret_cast<const float4*>(g.bias + col);
     const float4* s4 = reinterpret_cast<const float4*>(g.ln_s + col);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < NC / 4; ++i) {
 #ifdef SOME_DIAG_LNC_NOS       // timing experiment only (wrong results)
       const float4 b = __ldg(b4 + i), s = b;
 #else
@@ -426,54 +438,57 @@ __device__ __forceinline__ void ln_row_coeffs(const GemmParams& p, const GemmGro
 // EPI = SOME_EPI_STORE_BF16 / SILU_BF16 / GLU_BF16; kLn = LayerNorm-folded consumer (SOME_EPI_LN_*).
 template <int EPI, bool kLn>
 __device__ __forceinline__ void epilogue_warp_staged(const GemmParams& p, const GemmGroup& g, int row_base, int lane,
-                                                     uint32_t t_row, int col0, int col_tile, uint8_t* stage) {
+                                                     uint32_t t_row, int col0, int col_tile, StageRing& ring) {
   const int r = lane;  // row inside the warp's 32-row slab == TMEM lane offset
   uint64_t ra2 = 0, nmu2 = 0;
   if constexpr (kLn) ln_row_coeffs(p, g, row_base + r, ra2, nmu2);
-  if constexpr (EPI == SOME_EPI_STORE_BF16 || EPI == SOME_EPI_SILU_BF16) {
-#pragma unroll 1
-    for (int sc = 0; sc < 2; ++sc) {  // 64 accumulator columns -> 64 bf16 = one 128-byte staged row
-      const int c = col0 + sc * 64;
+  // The warp's 128 accumulator columns go through in eight 16-column granules with the tcgen05.ld of granule i + 1 in flight
+  // while granule i is processed (these epilogues are latency bound: one warp per 32 rows, the K = 512 GEMMs spend more
+  // time here than in their mainloop; a serial ld -> wait -> math chain per 32 columns cost ~20 %).
+  uint32_t a0[16], a1[16];
+  tmem_ld_32x16(t_row + col0, a0);
+  [[maybe_unused]] uint64_t keep[8];   // GLU: the "out" half of a packed 32-column group waits here for its gates
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t acc[32];
-        tmem_ld_32x32(t_row + c + hf * 32, acc);
-        tmem_ld_wait();
-        uint64_t v[16];
-        bias_or_ln32<kLn>(g, col_tile + c + hf * 32, acc, v, ra2, nmu2);
-        if constexpr (EPI == SOME_EPI_SILU_BF16) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = silu_fast2(v[i]);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(stage + stage_off(r, hf * 4 + q)) =
-              make_uint4(pack_bf16x2(v[4 * q]), pack_bf16x2(v[4 * q + 1]), pack_bf16x2(v[4 * q + 2]), pack_bf16x2(v[4 * q + 3]));
-      }
-      __syncwarp();
-      stage_flush(p, g, row_base, lane, stage, (size_t)(col_tile + c) * 2);
-      __syncwarp();
+  for (int gi = 0; gi < 8; ++gi) {
+    tmem_ld_wait();
+    if (gi + 1 < 8) {
+      if (gi & 1) tmem_ld_32x16(t_row + col0 + 16 * (gi + 1), a0);
+      else tmem_ld_32x16(t_row + col0 + 16 * (gi + 1), a1);
     }
-  } else {
-    static_assert(EPI == SOME_EPI_GLU_BF16, "staged epilogue: STORE / SILU / GLU only");
-    // 128 packed columns (4 x [16 out | 16 gate]) -> 64 bf16 outputs = one staged row
+    uint64_t v[8];
+    if (gi & 1) bias_or_ln32<kLn, 16>(g, col_tile + col0 + 16 * gi, a1, v, ra2, nmu2);
+    else bias_or_ln32<kLn, 16>(g, col_tile + col0 + 16 * gi, a0, v, ra2, nmu2);
+    if constexpr (EPI == SOME_EPI_STORE_BF16 || EPI == SOME_EPI_SILU_BF16) {
+      if constexpr (EPI == SOME_EPI_SILU_BF16) {
 #pragma unroll
-    for (int sub = 0; sub < 4; ++sub) {
-      uint32_t acc[32];
-      tmem_ld_32x32(t_row + col0 + sub * 32, acc);
-      tmem_ld_wait();
-      uint64_t v[16];
-      bias_or_ln32<kLn>(g, col_tile + col0 + sub * 32, acc, v, ra2, nmu2);
-      uint32_t o[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(f2_mul(v[i], sigmoid_fast2(v[8 + i])));
+        for (int i = 0; i < 8; ++i) v[i] = silu_fast2(v[i]);
+      }
+      // 16 columns -> 16 bf16 = two 16-byte cells of the 128-byte staged row (64 columns per row)
+      if ((gi & 3) == 0) ring.acquire(lane);
+      uint8_t* stage = ring.tile();
 #pragma unroll
       for (int q = 0; q < 2; ++q)
-        *reinterpret_cast<uint4*>(stage + stage_off(r, sub * 2 + q)) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        *reinterpret_cast<uint4*>(stage + stage_off(r, (gi & 3) * 2 + q)) =
+            make_uint4(pack_bf16x2(v[4 * q]), pack_bf16x2(v[4 * q + 1]), pack_bf16x2(v[4 * q + 2]), pack_bf16x2(v[4 * q + 3]));
+      if ((gi & 3) == 3) ring.flush(lane, col_tile + col0 + 64 * (gi >> 2), row_base);
+    } else {
+      static_assert(EPI == SOME_EPI_GLU_BF16, "staged epilogue: STORE / SILU / GLU only");
+      // packed columns: even granule = 16 "out" channels, odd granule = their 16 gates -> 16 bf16 outputs = two cells
+      if ((gi & 1) == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) keep[i] = v[i];
+      } else {
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(f2_mul(keep[i], sigmoid_fast2(v[i])));
+        if (gi == 1) ring.acquire(lane);
+        uint8_t* stage = ring.tile();
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+          *reinterpret_cast<uint4*>(stage + stage_off(r, (gi >> 1) * 2 + q)) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      }
+      if (gi == 7) ring.flush(lane, (col_tile + col0) >> 1, row_base);
     }
-    __syncwarp();
-    stage_flush(p, g, row_base, lane, stage, (size_t)((col_tile + col0) >> 1) * 2);
-    __syncwarp();
   }
 }
 
@@ -511,8 +526,8 @@ struct PairCfg {
   static constexpr bool LNC = EPI == SOME_EPI_LN_STORE_BF16 || EPI == SOME_EPI_LN_SILU_BF16 || EPI == SOME_EPI_LN_GLU_BF16;
   static constexpr int BASE = LNC ? EPI - SOME_EPI_LN_STORE_BF16 : EPI;   // staged epilogues: STORE / SILU / GLU
   static constexpr int STAGES = LNP ? 4 : 5;
-  // per epilogue warp: one 32 x 128 B transposition tile, or two residual slabs (+ the bf16 tile of the LN producers)
-  static constexpr int WARP_BYTES = TMA_EPI ? (LNP ? 12288 : 8192) : 4096;
+  // per epilogue warp: two 32 x 128 B output tiles, or two residual slabs (+ the bf16 tile of the LN producers)
+  static constexpr int WARP_BYTES = TMA_EPI ? (LNP ? 12288 : 8192) : 8192;   // staged: two alternating 4 KB tiles
   static constexpr int EPI_BYTES = EPI_WARPS * WARP_BYTES;
   static constexpr int SMEM = STAGES * PAIR_STAGE_BYTES + EPI_BYTES + 1024 + PAIR_BAR_BYTES;
   static_assert(SMEM <= 232448, "gemm_pair_kernel: shared memory over the 227 KB per-CTA limit");
@@ -775,11 +790,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       if (lane == 0) bulk_wait_group_read<0>();   // shared memory must outlive the last TMA stores' reads
     } else {
+      StageRing ring{epi_stage + ew * Cfg::WARP_BYTES, nullptr, 0};
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int grp = tile / tiles_per_group;
         const int t = tile - grp * tiles_per_group;
         const int m_blk = t / num_n, n_blk = t - m_blk * num_n;
         const GemmGroup& g = p.g[grp];
+        ring.map = grp == 0 ? &em.o[0] : &em.o[1];
         const int row_base = m_blk * 2 * BLOCK_M + rank * BLOCK_M + quad * 32;
         if constexpr (Cfg::LNC) {
           // The row statistics of the NEXT tile are pulled into L2 now: read at the start of that tile's epilogue they would
@@ -795,8 +812,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after_sync();
         const uint32_t t_row = tmem_base + acc * PAIR_BN + (static_cast<uint32_t>(quad * 32) << 16);
-        epilogue_warp_staged<Cfg::BASE, Cfg::LNC>(p, g, row_base, lane, t_row, half * COLS_PER_WARP, n_blk * PAIR_BN,
-                                                  epi_stage + ew * 4096);
+        epilogue_warp_staged<Cfg::BASE, Cfg::LNC>(p, g, row_base, lane, t_row, half * COLS_PER_WARP, n_blk * PAIR_BN, ring);
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
@@ -805,6 +821,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           acc_phase ^= 1;
         }
       }
+      if (lane == 0) bulk_wait_group_read<0>();   // shared memory must outlive the last TMA stores' reads
     }
   }
 
@@ -911,6 +928,11 @@ extern "C" int some_gemm(const some_gemm_args* a, cudaStream_t stream) {
                      "some_gemm: LayerNorm producer epilogue %d needs out_bf16 and ln_stats (group %d)", epi, s);
         if (make_tmap_2d(&em.xb[g], 2, a->out_bf16[s], a->M, out_cols, a->ld_out, 32, 64)) return -1;
       }
+    }
+    if (!head && !needs_resid) {   // staged bf16 epilogues: TMA-stored 32-row x 64-column tiles
+      const int out_cols = (epi == SOME_EPI_GLU_BF16 || epi == SOME_EPI_LN_GLU_BF16) ? a->N / 2 : a->N;
+      SOME_REQUIRE(a->ld_out % 8 == 0 && out_cols <= a->ld_out, "some_gemm: bad ld_out %d for %d bf16 output columns", a->ld_out, out_cols);
+      if (make_tmap_2d(&em.o[g], 2, a->out[s], a->M, out_cols, a->ld_out, 32, 64)) return -1;
     }
     if (ln_consumer)
       SOME_REQUIRE(a->ln_s[s] != nullptr && a->ln_stats[s] != nullptr && a->bias[s] != nullptr,

@@ -124,7 +124,9 @@ class Engine:
         SiLU outputs, i.e. by the weights, and white noise calibrates equally well; with folded LayerNorms the operand is the
         normalised row itself and a voice-like signal matters: residual -7e-5 vs -1.5e-4) runs through the sequencer, which
         records the column means of every GEMM's effective operand (some_forward, `calib`), and each layer's bias absorbs
-        (W_master - bf16(W)) . mean.  After it the mean error of `bounds` is ~3e-5 and zero-mean rounding noise remains."""
+        (W_master - bf16(W)) . mean.  After it the mean error of `bounds` is within +-1e-4 (clip dependent, +-3e-5 on most
+        clips) and zero-mean rounding noise remains.  (A second, head-level calibration against the library's own fp32 path
+        was tried and removed: what is left after this step depends on the input, not on the weights.)"""
         reg = getattr(self.w, 'rounding', None)
         if reg is None:
             return
@@ -329,7 +331,8 @@ class Engine:
     # the split is geometric: a small first chunk gets the GPU going, the later ones stay big.
     CHUNK_FRACTIONS = (0.125, 0.375, 0.5)
     MIN_CHUNK_FRAMES = 16384
-    GRAPH_MAX_FRAMES = 12288      # chunks up to this many frames go through CUDA-graph replay (SOME_B200_GRAPHS=0 disables)
+    GRAPH_MAX_FRAMES = 1024       # chunks up to this many frames (one ~10 s clip) go through CUDA-graph replay: -17 % device
+                                  # time at 862 frames, no gain beyond ~2000 (measured); SOME_B200_GRAPHS=0 disables
 
     def _graphed(self, key, fn):
         """Runs ``fn`` (kernel launches on the current stream, no allocation, no sync) through a cached CUDA graph: eager the

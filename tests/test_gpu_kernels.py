@@ -300,7 +300,7 @@ def test_dwconv_bn_silu(lib):
             r0 += t
 
 
-@pytest.mark.parametrize('impl', ['some_attention_varlen', 'some_attention_varlen_mma'])
+@pytest.mark.parametrize('impl', ['some_attention_varlen'])
 @pytest.mark.parametrize('frames', [[1], [64, 65, 127, 128, 129], [700, 3, 259], [2584]])
 def test_attention_varlen(lib, frames, impl):
     torch.manual_seed(7)

@@ -10,14 +10,14 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-OUT = os.path.join(HERE, '_trace', 'libattn_trace.so')
+OUT = os.environ.get('ATTN_TRACE_OUT', os.path.join(HERE, '_trace', 'libattn_trace.so'))
 
 
 def build():
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     src = os.path.join(ROOT, 'some_b200', 'csrc')
     subprocess.check_call(['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
-                           '-DSOME_ATTN_TRACE', '-Xcompiler', '-fPIC', '-shared', '-o', OUT,
+                           '-DSOME_ATTN_TRACE', *os.environ.get('ATTN_TRACE_FLAGS', '').split(), '-Xcompiler', '-fPIC', '-shared', '-o', OUT,
                            os.path.join(src, 'attention_tc.cu'), os.path.join(src, 'host_common.cu'), '-lcudart'])
 
 
@@ -48,29 +48,29 @@ def run():
     t = trace.cpu().numpy().reshape(4, 64, 4)
     t0 = t[t > 0].min()
     n = (T + 63) // 64
-    print('tile | grp: s_full  max_done exp_done arrived | mma: p_full_seen pv_issued qk_issued   (SM clocks since first event)')
-    for j in range(min(n, 24)):
+    print('tile | grp: s_full  max_done exp_done arrived | mma: before_p_full_wait  p_full_seen  pv_issued  qk_issued+commits   (SM clocks)')
+    for j in range(min(n, 20)):
         g = j & 1
         e = t[g, j] - t0
         m = t[2, j] - t0
-        print(f'{j:4d} |  {"AB"[g]}: {e[0]:7d} {e[1]:7d} {e[2]:7d} {e[3]:7d} | {m[0]:7d} {m[1]:7d} {m[2]:7d}')
+        print(f'{j:4d} |  {"AB"[g]}: {e[0]:7d} {e[1]:7d} {e[2]:7d} {e[3]:7d} | {m[0]:7d} {m[1]:7d} {m[2]:7d} {m[3]:7d}')
     for g in range(2):
         js = np.arange(g + 4, min(n, 40), 2)
         per = np.diff(t[g, js, 0]).mean()
         wait = (t[g, js[1:], 0] - t[g, js[:-1], 3]).mean()
         mx = (t[g, js, 1] - t[g, js, 0]).mean()
         ex = (t[g, js, 2] - t[g, js, 1]).mean()
-        print(f'group {"AB"[g]}: period {per:.0f} clk/tile, wait-for-S {wait:.0f}, max pass {mx:.0f}, exp pass {ex:.0f}')
-    js = np.arange(4, min(n, 40))
+        st = (t[g, js, 3] - t[g, js, 2]).mean()
+        print(f'group {"AB"[g]}: period {per:.0f} clk/tile, wait-for-S {wait:.0f}, max pass {mx:.0f}, exp pass {ex:.0f}, store+arrive {st:.0f}')
     js = np.arange(4, min(n - 2, 38))
-    print(f'mma thread (tile j): pv issued -> kv_full(j+2) passed {np.mean(t[3, js, 0] - t[2, js, 1]):.0f}, -> 1st qk mma issued '
-          f'{np.mean(t[3, js, 1] - t[3, js, 0]):.0f}, -> 4th {np.mean(t[3, js, 2] - t[3, js, 1]):.0f}, -> commit {np.mean(t[3, js, 3] - t[3, js, 2]):.0f}')
-    print(f'mma thread: p_full->pv issued {np.mean(t[2, js, 1] - t[2, js, 0]):.0f}, pv->qk issued {np.mean(t[2, js, 2] - t[2, js, 1]):.0f}, '
-          f'idle before p_full {np.mean(t[2, js[1:], 0] - t[2, js[:-1], 2]):.0f}')
+    m = t[2]
+    print(f'mma thread per tile: idle in p_full wait {np.mean(m[js, 1] - m[js, 0]):.0f}, PV issue (4 MMAs) {np.mean(m[js, 2] - m[js, 1]):.0f}, '
+          f'QK issue + 2 commits {np.mean(m[js, 3] - m[js, 2]):.0f}, kv_full wait etc. until next p_full wait {np.mean(m[js[1:], 0] - m[js[:-1], 3]):.0f}, '
+          f'period {np.mean(np.diff(m[js, 0])):.0f}')
     for g in range(2):
-        js = np.arange(g + 4, min(n, 40), 2)
-        print(f'group {"AB"[g]}: arrive -> mma saw p_full {np.mean(t[2, js, 0] - t[g, js, 3]):.0f} clk; '
-              f'qk(j+2) issued -> s_full(j+2) seen {np.mean(t[g, js[1:], 0] - t[2, js[:-1], 2]):.0f} clk')
+        js = np.arange(g + 4, min(n - 2, 38), 2)
+        print(f'group {"AB"[g]}: first-warp arrive -> mma saw p_full {np.mean(m[js, 1] - t[g, js, 3]):.0f} clk; '
+              f'qk(j+2) issued+committed -> s_full(j+2) seen by the group {np.mean(t[g, js + 2, 0] - m[js, 3]):.0f} clk')
 
 
 if __name__ == '__main__':
