@@ -1,0 +1,452 @@
+// EXPERIMENTAL (built only by tools/ab_bench.py --src): attention v8.
+//
+// v6b (some_b200/csrc/attention_tc.cu) leaves every softmax group idle ~35 % of its period: a group owns ONE S buffer, so the
+// chain  arrive -> PV_j -> QK_{j+2} -> s_full  (~950 clk) is exposed once per tile (profiles/r02_attention_notes.txt).  A second
+// S buffer per group does not fit beside two O accumulators in 256 TMEM columns.  v8 makes both groups accumulate into ONE
+// O (they share the per-row reference maximum R, so all P are on the same scale) and spends the freed 64 columns on a THIRD S
+// buffer: tiles rotate through S0 | S1 | S2, tile j = buffer j % 3, group j & 1; QK_{j+3} refills a buffer right behind PV_j,
+// so a group's next tile was issued half a period before it is needed.
+//
+// The shared reference maximum only ever changes at a CTA-wide rendezvous (rare after the first tiles): a warp that sees a
+// score exceed R by more than 2^8 raises sync_flag and waits at a named barrier; every other softmax warp joins from its next
+// safe point (the s_full polling loop or the drain loop at the end); the MMA thread is asked to quiesce (tcgen05.commit on a
+// dedicated barrier) and parks; the rows' new maxima are exchanged through shared memory, O and the row sums are rescaled,
+// and everything resumes.  Between rendezvous R is fixed, p = 2^((s - R) c) <= 2^8.
+#include "../../some_b200/csrc/host_common.h"
+#include "../../some_b200/csrc/sm100_ptx.cuh"
+
+#include "../../include/some_b200.h"
+
+namespace some {
+
+constexpr int TC_BM = 128;                 // queries per CTA
+constexpr int TC_BN = 64;                  // keys per tile
+constexpr int TC_QTILE = 128 * 64 * 2;     // 16 KB
+constexpr int TC_KTILE = TC_BN * 64 * 2;   // 8 KB (K or V tile)
+constexpr int TC_STAGES = 5;
+constexpr int TC_THREADS = 320;
+constexpr int TC_BAR_BYTES = 256;
+constexpr int TC_SMEM = TC_QTILE + TC_STAGES * 2 * TC_KTILE + TC_BAR_BYTES + 2 * TC_BM * 4 /*mxs*/ + 2 * TC_BM * 4 /*row sums*/ + 64;
+constexpr uint32_t TC_TMEM_COLS = 256;
+constexpr uint32_t TC_O_COL = 192;         // S0 | S1 | S2 | O
+
+struct AttnTcParams {
+  __nv_bfloat16* out[2];
+  const int32_t* cu_frames;
+  int tiles_per_clip;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 2^x for a packed pair on the FMA / ALU pipes (see attention_tc.cu)
+__device__ __forceinline__ void exp2_poly2(uint64_t y2, float& p0, float& p1) {
+  float a, b;
+  f2_unpack(y2, a, b);
+  a = fmaxf(a, -126.f);
+  b = fmaxf(b, -126.f);
+  const uint64_t y = f2_pack(a, b);
+  const uint64_t xf = f2_add(y, f2_pack(12582912.f, 12582912.f));
+  const uint64_t n = f2_add(xf, f2_pack(-12582912.f, -12582912.f));
+  const uint64_t r = f2_fma(n, f2_pack(-1.f, -1.f), y);
+  uint64_t q = f2_fma(f2_pack(0.05508868396282196f, 0.05508868396282196f), r, f2_pack(0.24260404706001282f, 0.24260404706001282f));
+  q = f2_fma(q, r, f2_pack(0.6932762265205383f, 0.6932762265205383f));
+  q = f2_fma(q, r, f2_pack(0.9999289512634277f, 0.9999289512634277f));
+  float qa, qb, xa, xb;
+  f2_unpack(q, qa, qb);
+  f2_unpack(xf, xa, xb);
+  p0 = __int_as_float(__float_as_int(qa) + (__float_as_int(xa) << 23));
+  p1 = __int_as_float(__float_as_int(qb) + (__float_as_int(xb) << 23));
+}
+#ifndef TC_POLY_OF_8
+#define TC_POLY_OF_8 2
+#endif
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_constant__ CUtensorMap tmkv0,
+                    const __grid_constant__ CUtensorMap tmq1, const __grid_constant__ CUtensorMap tmkv1,
+                    const AttnTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + TC_QTILE;                                  // stage s: K at +s * 2 * KTILE, V right after it
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + TC_STAGES * 2 * TC_KTILE);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;                      // [TC_STAGES]
+  uint64_t* kv_empty = kv_full + TC_STAGES;          // [TC_STAGES]
+  uint64_t* s_full = kv_empty + TC_STAGES;           // [3]  S buffer b holds Q K_j^T (tcgen05.commit)
+  uint64_t* p_full = s_full + 3;                     // [3]  P_j written over the head of buffer b (4 warp arrivals)
+  uint64_t* all_done = p_full + 3;                   // every PV retired
+  uint64_t* sync_req = all_done + 1;                 // rendezvous: softmax -> MMA thread "quiesce please"
+  uint64_t* quiesce = sync_req + 1;                  // MMA thread -> softmax: every MMA issued so far has retired
+  uint64_t* resume = quiesce + 1;                    // softmax -> MMA thread: go on
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resume + 1);
+  static_assert(8 * (1 + 2 * TC_STAGES + 10 + 1) <= TC_BAR_BYTES, "barrier block too small");
+  float* mxs = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + TC_BAR_BYTES);   // [2][128] row maxima offered at a rendezvous
+  float* lsum = mxs + 2 * TC_BM;                                                             // [2][128] final row sums
+  volatile int* sync_flag = reinterpret_cast<volatile int*>(lsum + 2 * TC_BM);               // a rendezvous has been requested
+  volatile int* done_cnt = sync_flag + 1;                                                    // softmax warps that finished their tiles
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int clip = blockIdx.x / p.tiles_per_clip;
+  const int qt = blockIdx.x - clip * p.tiles_per_clip;
+  const int row_begin = p.cu_frames[clip];
+  const int T = p.cu_frames[clip + 1] - row_begin;
+  const int q0 = qt * TC_BM;
+  if (q0 >= T) return;  // whole CTA, before any barrier / TMEM use
+  const int head = blockIdx.y;
+  const int grp = blockIdx.z;
+  const CUtensorMap* tmq = grp == 0 ? &tmq0 : &tmq1;
+  const CUtensorMap* tmkv = grp == 0 ? &tmkv0 : &tmkv1;
+  const int n_tiles = (T + TC_BN - 1) / TC_BN;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) {
+      printf("some_b200: attention smem base not 1024-byte aligned\n");
+      __trap();
+    }
+    tma_prefetch_desc(tmq);
+    tma_prefetch_desc(tmkv);
+    *sync_flag = 0;
+    *done_cnt = 0;
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < TC_STAGES; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+    }
+    mbar_init(all_done, 1);
+    mbar_init(sync_req, 1);
+    mbar_init(quiesce, 1);
+    mbar_init(resume, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<TC_TMEM_COLS>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(q_full, TC_QTILE);
+      tma_load_2d(sQ, tmq, q_full, head * 64, row_begin + q0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], 2 * TC_KTILE);
+        uint8_t* dst = sKV + s * 2 * TC_KTILE;
+        tma_load_2d(dst, tmkv, &kv_full[s], SOME_DIM + head * 64, row_begin + j * TC_BN);
+        tma_load_2d(dst + TC_KTILE, tmkv, &kv_full[s], 2 * SOME_DIM + head * 64, row_begin + j * TC_BN);
+        if (++s == TC_STAGES) s = 0, ph ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc_qk = umma_idesc_bf16_f32(TC_BM, TC_BN);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16_f32(TC_BM, 64, 0, 1);  // B = V is MN-major
+      const uint64_t qdesc = umma_desc_kmajor_sw128(smem_u32(sQ));
+      auto wait_kv = [&](int t) {
+        mbar_wait(&kv_full[t % TC_STAGES], (t / TC_STAGES) & 1);
+        tc_fence_after_sync();
+      };
+      auto issue_qk = [&](int t) {  // S[t % 3] = Q K_t^T   (kv_full[t] already awaited)
+        const int s = t % TC_STAGES;
+        const uint64_t kdesc = umma_desc_kmajor_sw128(smem_u32(sKV + s * 2 * TC_KTILE));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tmem_base + (t % 3) * TC_BN, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+        umma_commit(&s_full[t % 3]);
+      };
+      mbar_wait(q_full, 0);
+      for (int t = 0; t < 3 && t < n_tiles; ++t) {
+        wait_kv(t);
+        issue_qk(t);
+      }
+      uint32_t served = 0;   // rendezvous served so far
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % TC_STAGES, b = j % 3;
+        if (j + 3 < n_tiles) wait_kv(j + 3);      // off the critical path: before the p_full wait
+        // wait for P_j, serving rendezvous requests meanwhile (quiesce: everything issued so far retires; park until resumed)
+        {
+          uint32_t spins = 0;
+          while (!mbar_try_wait(&p_full[b], (j / 3) & 1)) {
+            if (mbar_try_wait(sync_req, served & 1)) {
+              umma_commit(quiesce);
+              mbar_wait(resume, served & 1);
+              tc_fence_after_sync();          // O was rescaled with tcgen05.st by the softmax warps
+              ++served;
+            }
+            if (++spins == (1u << 24)) {
+              printf("some_b200: attention v8 p_full timeout block %d tile %d\n", (int)blockIdx.x, j);
+              __trap();
+            }
+          }
+        }
+        tc_fence_after_sync();
+        const uint64_t vdesc = umma_desc_mnmajor_sw128(smem_u32(sKV + s * 2 * TC_KTILE + TC_KTILE), 1024);
+        const uint32_t p_tmem = tmem_base + b * TC_BN;  // P_j (bf16, two keys per column) over the first 32 columns of its S buffer
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // 16 keys per MMA: A +8 TMEM columns, B +16 key rows = 2 KB (+128)
+          umma_bf16_ts(tmem_base + TC_O_COL, p_tmem + 8 * k, vdesc + 128 * k, idesc_pv, j > 0 || k != 0);
+        if (j + 3 < n_tiles) issue_qk(j + 3);     // the buffer just consumed is refilled three tiles ahead
+        umma_commit(&kv_empty[s]);
+      }
+      umma_commit(all_done);
+    }
+    __syncwarp();
+  } else {
+    const int g = (warp - 2) >> 2;  // softmax group: 0 = even key tiles, 1 = odd key tiles
+    const int quad = warp & 3;      // the TMEM lane quadrant this warp may touch
+    const int r = quad * 32 + lane; // query row inside the tile == TMEM lane
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const uint32_t t_o = t_lane + TC_O_COL;
+    const float c = 0.125f * 1.4426950408889634f;  // dim_head^-0.5 * log2(e)
+    const uint64_t c2 = f2_pack(c, c);
+    float R = -INFINITY;   // shared reference maximum of this row (identical in both groups: it only changes at a rendezvous)
+    float l = 0.f;         // this group's part of the row sum, relative to R
+    uint32_t epoch = 0;    // rendezvous completed
+
+    // CTA-wide rendezvous of the eight softmax warps (+ the parked MMA thread).  offer = the row maximum this thread wants
+    // the reference raised to (R itself when it has nothing to ask for).
+    auto rendezvous = [&](float offer) {
+      mxs[g * TC_BM + r] = offer;
+      __syncwarp();
+      asm volatile("bar.sync 2, 256;" ::: "memory");            // every softmax warp is here: no new P arrivals from now on
+      if (warp == 2 && lane == 0) {
+        *sync_flag = 0;                                          // requests raised after this point start a new rendezvous
+        mbar_arrive(sync_req);
+      }
+      mbar_wait(quiesce, epoch & 1);                             // every MMA issued so far has retired: O is quiescent
+      tc_fence_after_sync();
+      const float Rn = fmaxf(fmaxf(mxs[r], mxs[TC_BM + r]), R);
+      const float alpha = (R == -INFINITY) ? 0.f : ex2_approx((R - Rn) * c);
+      const bool touch_o = (R != -INFINITY) && (alpha != 1.0f);
+      R = Rn;
+      l *= alpha;
+      if (g == 0 && __any_sync(0xffffffffu, touch_o)) {          // O rows of this quadrant *= alpha (group 0's warps own the job)
+        uint32_t o[32];
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          tmem_ld_32x32(t_o + 32 * h, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_32x32(t_o + 32 * h, o);
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");            // O rescaled, maxima consumed
+      if (warp == 2 && lane == 0) mbar_arrive(resume);
+      ++epoch;
+    };
+    // wait on an mbarrier from a point where joining a rendezvous is safe
+    auto wait_joining = [&](uint64_t* bar, uint32_t parity) {
+      uint32_t spins = 0;
+      while (!mbar_try_wait(bar, parity)) {
+        if (*sync_flag) rendezvous(R);
+        if (++spins == (1u << 24)) {
+          printf("some_b200: attention v8 softmax wait timeout block %d warp %d\n", (int)blockIdx.x, warp);
+          __trap();
+        }
+      }
+    };
+
+    for (int j = g; j < n_tiles; j += 2) {
+      const int b = j % 3;
+      const uint32_t t_s = t_lane + b * TC_BN;
+      const int valid = min(TC_BN, T - j * TC_BN);  // keys of this tile inside the clip
+      wait_joining(&s_full[b], (j / 3) & 1);
+      tc_fence_after_sync();
+      uint32_t v[32];
+      // ---- pass 1: row maximum (the scores are re-read from tensor memory in pass 2)
+      float mx = -INFINITY;
+      {
+        uint32_t u[32];
+        tmem_ld_32x32(t_s, v);
+        tmem_ld_32x32(t_s + 32, u);
+        tmem_ld_wait();
+        if (valid == TC_BN) {
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+          float m4 = -INFINITY, m5 = -INFINITY, m6 = -INFINITY, m7 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+            m2 = fmaxf(m2, fmaxf(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])));
+            m3 = fmaxf(m3, fmaxf(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
+            m4 = fmaxf(m4, fmaxf(__uint_as_float(u[i]), __uint_as_float(u[i + 1])));
+            m5 = fmaxf(m5, fmaxf(__uint_as_float(u[i + 2]), __uint_as_float(u[i + 3])));
+            m6 = fmaxf(m6, fmaxf(__uint_as_float(u[i + 4]), __uint_as_float(u[i + 5])));
+            m7 = fmaxf(m7, fmaxf(__uint_as_float(u[i + 6]), __uint_as_float(u[i + 7])));
+          }
+          mx = fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), fmaxf(fmaxf(m4, m5), fmaxf(m6, m7)));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+            if (32 + i < valid) mx = fmaxf(mx, __uint_as_float(u[i]));
+          }
+        }
+      }
+      // ---- the reference maximum may only move at a rendezvous (warp-uniform decision; R = -inf on the very first tile)
+      while (__any_sync(0xffffffffu, (mx - R) * c > 8.0f || R == -INFINITY)) {
+        if (lane == 0) *sync_flag = 1;
+        rendezvous(fmaxf(R, mx));
+      }
+      const float mc = R * c;
+      const uint64_t nmc2 = f2_pack(-mc, -mc);
+      // ---- pass 2: p = 2^(s c - R c), row sum, bf16 pack
+      uint32_t pk[32];
+      uint64_t rs_a = f2_pack(0.f, 0.f), rs_b = rs_a;
+      auto quarter = [&](const uint32_t(&x)[16], int q) {
+        if (valid == TC_BN) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const uint64_t ya = f2_fma(f2_pack(__uint_as_float(x[i]), __uint_as_float(x[i + 1])), c2, nmc2);
+            const uint64_t yb = f2_fma(f2_pack(__uint_as_float(x[i + 2]), __uint_as_float(x[i + 3])), c2, nmc2);
+            float p0, p1, p2, p3;
+            {
+              float y0, y1;
+              f2_unpack(ya, y0, y1);
+              p0 = ex2_approx(y0);
+              p1 = ex2_approx(y1);
+            }
+            if (TC_POLY_OF_8 >= 4 || ((i & 4) && TC_POLY_OF_8 >= 2)) {
+              exp2_poly2(yb, p2, p3);
+            } else {
+              float y2, y3;
+              f2_unpack(yb, y2, y3);
+              p2 = ex2_approx(y2);
+              p3 = ex2_approx(y3);
+            }
+            rs_a = f2_add(rs_a, f2_pack(p0, p1));
+            rs_b = f2_add(rs_b, f2_pack(p2, p3));
+            pk[8 * q + (i >> 1)] = pack_bf16x2(p0, p1);
+            pk[8 * q + (i >> 1) + 1] = pack_bf16x2(p2, p3);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(x[i]), c, -mc));
+            float p1 = ex2_approx(fmaf(__uint_as_float(x[i + 1]), c, -mc));
+            if (16 * q + i >= valid) p0 = 0.f;
+            if (16 * q + i + 1 >= valid) p1 = 0.f;
+            rs_a = f2_add(rs_a, f2_pack(p0, p1));
+            pk[8 * q + (i >> 1)] = pack_bf16x2(p0, p1);
+          }
+        }
+      };
+      {
+        uint32_t xa[16], xb[16];
+        tmem_ld_32x16(t_s, xa);
+        tmem_ld_wait();
+        tmem_ld_32x16(t_s + 16, xb);
+        quarter(xa, 0);
+        tmem_ld_wait();
+        tmem_ld_32x16(t_s + 32, xa);
+        quarter(xb, 1);
+        tmem_ld_wait();
+        tmem_ld_32x16(t_s + 48, xb);
+        quarter(xa, 2);
+        tmem_ld_wait();
+        quarter(xb, 3);
+      }
+      {
+        float s0, s1, s2, s3;
+        f2_unpack(rs_a, s0, s1);
+        f2_unpack(rs_b, s2, s3);
+        l += (s0 + s1) + (s2 + s3);
+      }
+      // ---- P -> TMEM over the first 32 columns of this tile's S buffer; QK_{j+3} overwrites them only after PV_j
+      tmem_st_32x32(t_s, pk);
+      tmem_st_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[b]);
+    }
+    // ---- drain: keep serving rendezvous until every softmax warp has finished its tiles
+    __syncwarp();
+    if (lane == 0) atomicAdd(const_cast<int*>(done_cnt), 1);
+    {
+      uint32_t spins = 0;
+      while (*done_cnt < 8) {
+        if (*sync_flag) rendezvous(R);
+        if (++spins == (1u << 26)) {
+          printf("some_b200: attention v8 drain timeout block %d warp %d\n", (int)blockIdx.x, warp);
+          __trap();
+        }
+      }
+    }
+    // ---- O / (l_A + l_B) -> bf16 -> out[row, head * 64 ..]; group g writes channels [32 g, 32 g + 32)
+    lsum[g * TC_BM + r] = l;
+    mbar_wait(all_done, 0);
+    tc_fence_after_sync();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float inv = 1.0f / (lsum[r] + lsum[TC_BM + r]);
+    const int qrow = q0 + r;
+    __nv_bfloat16* dst = p.out[grp] + (size_t)(row_begin + qrow) * SOME_DIM + head * 64 + 32 * g;
+    uint32_t oa[32];
+    tmem_ld_32x32(t_o + 32 * g, oa);
+    tmem_ld_wait();
+    if (qrow < T) {
+      float o[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(oa[i]) * inv;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        reinterpret_cast<uint4*>(dst)[i] = make_uint4(pack_bf16x2(o[8 * i], o[8 * i + 1]), pack_bf16x2(o[8 * i + 2], o[8 * i + 3]),
+                                                      pack_bf16x2(o[8 * i + 4], o[8 * i + 5]), pack_bf16x2(o[8 * i + 6], o[8 * i + 7]));
+    }
+    tc_fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc<TC_TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace some
+
+using namespace some;
+
+extern "C" int some_attention_varlen(const some_attn_args* a, cudaStream_t stream) {
+  SOME_REQUIRE(a != nullptr && (a->groups == 1 || a->groups == 2), "some_attention_varlen: bad args");
+  if (a->B <= 0 || a->max_frames <= 0 || a->M <= 0) return 0;
+  SOME_REQUIRE(a->cu_frames != nullptr, "some_attention_varlen: null cu_frames");
+  AttnTcParams p;
+  CUtensorMap maps[4];
+  for (int g = 0; g < 2; ++g) {
+    const int s = g < a->groups ? g : 0;
+    SOME_REQUIRE(a->qkv[s] && a->out[s], "some_attention_varlen: null pointer in group %d", s);
+    if (make_tmap_bf16_2d(&maps[2 * g], a->qkv[s], a->M, 3 * SOME_DIM, 3 * SOME_DIM, TC_BM)) return -1;
+    if (make_tmap_bf16_2d(&maps[2 * g + 1], a->qkv[s], a->M, 3 * SOME_DIM, 3 * SOME_DIM, TC_BN)) return -1;
+    p.out[g] = reinterpret_cast<__nv_bfloat16*>(a->out[s]);
+  }
+  p.cu_frames = a->cu_frames;
+  p.tiles_per_clip = (a->max_frames + TC_BM - 1) / TC_BM;
+  static bool configured[kMaxDevices] = {};   // function attributes are per device
+  const int dev_ = device_index();
+  if (!configured[dev_]) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    SOME_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(attention_tc): %s", cudaGetErrorString(e));
+    e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    SOME_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(attention_tc carveout): %s", cudaGetErrorString(e));
+    configured[dev_] = true;
+  }
+  const long long gx = 1ll * p.tiles_per_clip * a->B;
+  SOME_REQUIRE(gx < (1ll << 31), "some_attention_varlen: grid too large");
+  dim3 grid(static_cast<unsigned>(gx), SOME_HEADS, a->groups);
+  attention_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+  return check_launch("some_attention_varlen");
+}
