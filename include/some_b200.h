@@ -275,6 +275,12 @@ typedef struct {
   uint16_t* xb[2];             /* bf16 [M,512] copy of the residual stream (ln_fold only) */
   float* ln_stats[2];          /* f32 [M][SOME_LN_SLOTS][2] (ln_fold only) */
 } some_workspace;
+/* Workspace sizing for hosts that do not use the Python engine: the number of bytes some_workspace needs for M rows (every
+ * buffer 256-byte aligned, ln_fold buffers included when ln_fold != 0), and a helper that carves ONE caller-allocated device
+ * block of that size into the struct (units / probs / bounds included).  Returns 0 / fills *ws on success. */
+uint64_t some_workspace_bytes(int M, int outdim, int ln_fold);
+int some_workspace_carve(void* device_block, uint64_t bytes, int M, int outdim, int ln_fold, some_workspace* ws);
+
 /* Optional per-launch timing of some_forward (bench.py's roofline pass): CUDA events on the launching stream around every
  * kernel the sequencer enqueues.  The library owns the events; read after the stream has been synchronised. */
 typedef struct some_profiler some_profiler;

@@ -128,6 +128,8 @@ EXPORTS = {
                                C.POINTER(CalibrationC), _vp]),
     'some_forward_f32': (C.c_int, [C.POINTER(ModelF32C), C.POINTER(WorkspaceF32C), C.c_int, C.c_int, _vp, C.c_int, C.c_int,
                                    _vp]),
+    'some_workspace_bytes': (C.c_uint64, [C.c_int, C.c_int, C.c_int]),
+    'some_workspace_carve': (C.c_int, [_vp, C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(WorkspaceC)]),
     'some_profiler_create': (C.c_int, [C.c_int, C.POINTER(_vp)]),
     'some_profiler_destroy': (C.c_int, [_vp]),
     'some_profiler_reset': (C.c_int, [_vp]),

@@ -69,6 +69,28 @@ def test_abi_struct_layouts_match_the_c_compiler(tmp_path):
         assert (int(out[2 * i]), int(out[2 * i + 1])) == (C.sizeof(cls), getattr(cls, last).offset), name
 
 
+def test_workspace_sizing_and_carving():
+    """some_workspace_bytes / some_workspace_carve: host-only arithmetic (no GPU needed): sizes add up, buffers are aligned and
+    disjoint, ln_fold adds exactly its two buffers per stream."""
+    import ctypes as C
+    from some_b200 import _lib
+    lib = _lib.load()
+    m, outdim = 1000, 129
+    n0, n1 = lib.some_workspace_bytes(m, outdim, 0), lib.some_workspace_bytes(m, outdim, 1)
+    al = lambda b: (b + 255) & ~255
+    want = 2 * al(m * 512 * 4) + 2 * al(m * 512 * 2) + 2 * al(m * 2048 * 2) + 2 * al(m * 1536 * 2) + 2 * al(m * 512 * 2) \
+        + al(m * 80 * 2) + al(m * outdim * 4) + al(m * 4)
+    assert n0 == want and n1 == want + 2 * al(m * 512 * 2) + 2 * al(m * 8 * 2 * 4)
+    ws = _lib.WorkspaceC()
+    base = 0x7f0000000000
+    assert lib.some_workspace_carve(C.c_void_p(base), n1, m, outdim, 1, C.byref(ws)) == 0
+    ptrs = sorted([ws.x[0], ws.x[1], ws.a[0], ws.a[1], ws.h[0], ws.h[1], ws.qkv[0], ws.qkv[1], ws.g[0], ws.g[1], ws.units, ws.probs,
+                   ws.bounds, ws.xb[0], ws.xb[1], ws.ln_stats[0], ws.ln_stats[1]])
+    assert ptrs[0] == base and all(p % 256 == 0 for p in ptrs) and len(set(ptrs)) == 17 and ptrs[-1] < base + n1
+    assert lib.some_workspace_carve(C.c_void_p(base), n1 - 1, m, outdim, 1, C.byref(ws)) != 0
+    assert b'too small' in lib.some_last_error()
+
+
 def test_engine_refuses_cpu():
     from some_b200 import _lib, plugin
     cfg = synth.named_config('two_head')

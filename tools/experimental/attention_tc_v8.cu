@@ -23,10 +23,10 @@ constexpr int TC_BM = 128;                 // queries per CTA
 constexpr int TC_BN = 64;                  // keys per tile
 constexpr int TC_QTILE = 128 * 64 * 2;     // 16 KB
 constexpr int TC_KTILE = TC_BN * 64 * 2;   // 8 KB (K or V tile)
-constexpr int TC_STAGES = 5;
+constexpr int TC_STAGES = 5;                // slots of the K ring AND of the V ring (8 KB each): K_t is needed three iterations before V_t
 constexpr int TC_THREADS = 320;
-constexpr int TC_BAR_BYTES = 256;
-constexpr int TC_SMEM = TC_QTILE + TC_STAGES * 2 * TC_KTILE + TC_BAR_BYTES + 2 * TC_BM * 4 /*mxs*/ + 2 * TC_BM * 4 /*row sums*/ + 64;
+constexpr int TC_BAR_BYTES = 320;
+constexpr int TC_SMEM = TC_QTILE + TC_STAGES * 2 * TC_KTILE + TC_BAR_BYTES + 2 * TC_BM * 4 /*mxs*/ + 2 * TC_BM * 4 /*row sums*/ + 64 /*flags, arrived[8]*/;
 constexpr uint32_t TC_TMEM_COLS = 256;
 constexpr uint32_t TC_O_COL = 192;         // S0 | S1 | S2 | O
 
@@ -70,23 +70,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
                     const AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
-  uint8_t* sKV = smem + TC_QTILE;                                  // stage s: K at +s * 2 * KTILE, V right after it
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + TC_STAGES * 2 * TC_KTILE);
+  uint8_t* sK = smem + TC_QTILE;                                   // K ring: slot t % TC_STAGES
+  uint8_t* sV = sK + TC_STAGES * TC_KTILE;                         // V ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + TC_STAGES * TC_KTILE);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;                      // [TC_STAGES]
-  uint64_t* kv_empty = kv_full + TC_STAGES;          // [TC_STAGES]
-  uint64_t* s_full = kv_empty + TC_STAGES;           // [3]  S buffer b holds Q K_j^T (tcgen05.commit)
+  uint64_t* k_full = bars + 1;                       // [TC_STAGES]
+  uint64_t* k_empty = k_full + TC_STAGES;            // [TC_STAGES]
+  uint64_t* v_full = k_empty + TC_STAGES;            // [TC_STAGES]
+  uint64_t* v_empty = v_full + TC_STAGES;            // [TC_STAGES]
+  uint64_t* s_full = v_empty + TC_STAGES;            // [3]  S buffer b holds Q K_j^T (tcgen05.commit)
   uint64_t* p_full = s_full + 3;                     // [3]  P_j written over the head of buffer b (4 warp arrivals)
   uint64_t* all_done = p_full + 3;                   // every PV retired
   uint64_t* sync_req = all_done + 1;                 // rendezvous: softmax -> MMA thread "quiesce please"
   uint64_t* quiesce = sync_req + 1;                  // MMA thread -> softmax: every MMA issued so far has retired
   uint64_t* resume = quiesce + 1;                    // softmax -> MMA thread: go on
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resume + 1);
-  static_assert(8 * (1 + 2 * TC_STAGES + 10 + 1) <= TC_BAR_BYTES, "barrier block too small");
+  static_assert(8 * (1 + 4 * TC_STAGES + 10 + 1) <= TC_BAR_BYTES, "barrier block too small");
   float* mxs = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + TC_BAR_BYTES);   // [2][128] row maxima offered at a rendezvous
   float* lsum = mxs + 2 * TC_BM;                                                             // [2][128] final row sums
   volatile int* sync_flag = reinterpret_cast<volatile int*>(lsum + 2 * TC_BM);               // a rendezvous has been requested
   volatile int* done_cnt = sync_flag + 1;                                                    // softmax warps that finished their tiles
+  volatile int* arrived = sync_flag + 2;                                                     // [8] last tile each softmax warp arrived p_full for
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int clip = blockIdx.x / p.tiles_per_clip;
@@ -114,8 +118,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < TC_STAGES; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
     }
     for (int i = 0; i < 3; ++i) {
       mbar_init(&s_full[i], 1);
@@ -137,15 +143,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
     if (elect_one_sync()) {
       mbar_arrive_expect_tx(q_full, TC_QTILE);
       tma_load_2d(sQ, tmq, q_full, head * 64, row_begin + q0);
-      int s = 0;
-      uint32_t ph = 0;
+      // load order = consumption order of the MMA thread: K_0 K_1 K_2, then (V_j, K_{j+3}) per iteration
+      auto load_k = [&](int t) {
+        const int s = t % TC_STAGES;
+        mbar_wait(&k_empty[s], ((t / TC_STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[s], TC_KTILE);
+        tma_load_2d(sK + s * TC_KTILE, tmkv, &k_full[s], SOME_DIM + head * 64, row_begin + t * TC_BN);
+      };
+      auto load_v = [&](int t) {
+        const int s = t % TC_STAGES;
+        mbar_wait(&v_empty[s], ((t / TC_STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[s], TC_KTILE);
+        tma_load_2d(sV + s * TC_KTILE, tmkv, &v_full[s], 2 * SOME_DIM + head * 64, row_begin + t * TC_BN);
+      };
+      for (int t = 0; t < 3 && t < n_tiles; ++t) load_k(t);
       for (int j = 0; j < n_tiles; ++j) {
-        mbar_wait(&kv_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], 2 * TC_KTILE);
-        uint8_t* dst = sKV + s * 2 * TC_KTILE;
-        tma_load_2d(dst, tmkv, &kv_full[s], SOME_DIM + head * 64, row_begin + j * TC_BN);
-        tma_load_2d(dst + TC_KTILE, tmkv, &kv_full[s], 2 * SOME_DIM + head * 64, row_begin + j * TC_BN);
-        if (++s == TC_STAGES) s = 0, ph ^= 1;
+        load_v(j);
+        if (j + 3 < n_tiles) load_k(j + 3);
       }
     }
     __syncwarp();
@@ -154,51 +168,65 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
       constexpr uint32_t idesc_qk = umma_idesc_bf16_f32(TC_BM, TC_BN);
       constexpr uint32_t idesc_pv = umma_idesc_bf16_f32(TC_BM, 64, 0, 1);  // B = V is MN-major
       const uint64_t qdesc = umma_desc_kmajor_sw128(smem_u32(sQ));
-      auto wait_kv = [&](int t) {
-        mbar_wait(&kv_full[t % TC_STAGES], (t / TC_STAGES) & 1);
-        tc_fence_after_sync();
-      };
-      auto issue_qk = [&](int t) {  // S[t % 3] = Q K_t^T   (kv_full[t] already awaited)
+      auto issue_qk = [&](int t) {  // S[t % 3] = Q K_t^T
         const int s = t % TC_STAGES;
-        const uint64_t kdesc = umma_desc_kmajor_sw128(smem_u32(sKV + s * 2 * TC_KTILE));
+        mbar_wait(&k_full[s], (t / TC_STAGES) & 1);
+        tc_fence_after_sync();
+        const uint64_t kdesc = umma_desc_kmajor_sw128(smem_u32(sK + s * TC_KTILE));
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16_ss(tmem_base + (t % 3) * TC_BN, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
         umma_commit(&s_full[t % 3]);
+        umma_commit(&k_empty[s]);
       };
       mbar_wait(q_full, 0);
-      for (int t = 0; t < 3 && t < n_tiles; ++t) {
-        wait_kv(t);
-        issue_qk(t);
-      }
-      uint32_t served = 0;   // rendezvous served so far
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j % TC_STAGES, b = j % 3;
-        if (j + 3 < n_tiles) wait_kv(j + 3);      // off the critical path: before the p_full wait
-        // wait for P_j, serving rendezvous requests meanwhile (quiesce: everything issued so far retires; park until resumed)
-        {
-          uint32_t spins = 0;
-          while (!mbar_try_wait(&p_full[b], (j / 3) & 1)) {
-            if (mbar_try_wait(sync_req, served & 1)) {
-              umma_commit(quiesce);
-              mbar_wait(resume, served & 1);
-              tc_fence_after_sync();          // O was rescaled with tcgen05.st by the softmax warps
-              ++served;
-            }
-            if (++spins == (1u << 24)) {
-              printf("some_b200: attention v8 p_full timeout block %d tile %d\n", (int)blockIdx.x, j);
-              __trap();
-            }
-          }
-        }
+      for (int t = 0; t < 3 && t < n_tiles; ++t) issue_qk(t);
+      // The two groups' tiles are served in whatever order their P becomes ready (no head-of-line blocking): nxt[g] = the
+      // group's next tile.  A rendezvous request is served only when neither group has a complete P waiting, so every P
+      // that is complete at the rendezvous has gone through its PV before O is rescaled.
+      int nxt[2] = {0, 1};
+      int remaining = n_tiles;
+      bool first = true;
+      uint32_t served = 0, spins = 0;
+      auto try_tile = [&](int g) -> bool {
+        const int j = nxt[g];
+        if (j >= n_tiles || !mbar_try_wait(&p_full[j % 3], (j / 3) & 1)) return false;
         tc_fence_after_sync();
-        const uint64_t vdesc = umma_desc_mnmajor_sw128(smem_u32(sKV + s * 2 * TC_KTILE + TC_KTILE), 1024);
+        const int s = j % TC_STAGES, b = j % 3;
+        mbar_wait(&v_full[s], (j / TC_STAGES) & 1);
+        tc_fence_after_sync();
+        const uint64_t vdesc = umma_desc_mnmajor_sw128(smem_u32(sV + s * TC_KTILE), 1024);
         const uint32_t p_tmem = tmem_base + b * TC_BN;  // P_j (bf16, two keys per column) over the first 32 columns of its S buffer
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // 16 keys per MMA: A +8 TMEM columns, B +16 key rows = 2 KB (+128)
-          umma_bf16_ts(tmem_base + TC_O_COL, p_tmem + 8 * k, vdesc + 128 * k, idesc_pv, j > 0 || k != 0);
+          umma_bf16_ts(tmem_base + TC_O_COL, p_tmem + 8 * k, vdesc + 128 * k, idesc_pv, !first || k != 0);
+        first = false;
+        umma_commit(&v_empty[s]);
         if (j + 3 < n_tiles) issue_qk(j + 3);     // the buffer just consumed is refilled three tiles ahead
-        umma_commit(&kv_empty[s]);
+        nxt[g] = j + 2;
+        --remaining;
+        return true;
+      };
+      while (remaining > 0) {
+        bool progressed = try_tile(0);
+        progressed |= try_tile(1);
+        if (progressed) {
+          spins = 0;
+          continue;
+        }
+        if (mbar_try_wait(sync_req, served & 1)) {
+          // every softmax warp is parked: no more arrivals.  Drain what completed since the last look, then quiesce.
+          while (try_tile(0) || try_tile(1)) {
+          }
+          umma_commit(quiesce);
+          mbar_wait(resume, served & 1);
+          tc_fence_after_sync();          // O (and pending P rows) were rewritten with tcgen05.st by the softmax warps
+          ++served;
+        }
+        if (++spins == (1u << 26)) {
+          printf("some_b200: attention v8 MMA thread timeout block %d (next tiles %d %d of %d)\n", (int)blockIdx.x, nxt[0], nxt[1], n_tiles);
+          __trap();
+        }
       }
       umma_commit(all_done);
     }
@@ -214,11 +242,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
     float R = -INFINITY;   // shared reference maximum of this row (identical in both groups: it only changes at a rendezvous)
     float l = 0.f;         // this group's part of the row sum, relative to R
     uint32_t epoch = 0;    // rendezvous completed
+    int my_arrived = -1;   // last tile this warp arrived p_full for
 
     // CTA-wide rendezvous of the eight softmax warps (+ the parked MMA thread).  offer = the row maximum this thread wants
     // the reference raised to (R itself when it has nothing to ask for).
     auto rendezvous = [&](float offer) {
       mxs[g * TC_BM + r] = offer;
+      if (lane == 0) arrived[warp - 2] = my_arrived;
       __syncwarp();
       asm volatile("bar.sync 2, 256;" ::: "memory");            // every softmax warp is here: no new P arrivals from now on
       if (warp == 2 && lane == 0) {
@@ -232,6 +262,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
       const bool touch_o = (R != -INFINITY) && (alpha != 1.0f);
       R = Rn;
       l *= alpha;
+      // A P row this warp has written whose PV has not been issued (a sibling warp of the group has not arrived for that
+      // tile yet: the MMA thread drained every COMPLETE tile before it quiesced) is still on the old scale: bring it along.
+      {
+        int gmin = my_arrived;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) gmin = min(gmin, arrived[4 * g + w]);
+        if (my_arrived > gmin && __any_sync(0xffffffffu, touch_o)) {
+          const uint32_t t_p = t_lane + (my_arrived % 3) * TC_BN;
+          uint32_t pp[32];
+          tmem_ld_32x32(t_p, pp);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float lo = __uint_as_float(pp[i] << 16) * alpha, hi = __uint_as_float(pp[i] & 0xffff0000u) * alpha;
+            pp[i] = pack_bf16x2(lo, hi);
+          }
+          tmem_st_32x32(t_p, pp);
+          tmem_st_wait();
+          tc_fence_before_sync();
+        }
+      }
       if (g == 0 && __any_sync(0xffffffffu, touch_o)) {          // O rows of this quadrant *= alpha (group 0's warps own the job)
         uint32_t o[32];
 #pragma unroll 1
@@ -373,6 +424,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[b]);
+      my_arrived = j;
     }
     // ---- drain: keep serving rendezvous until every softmax warp has finished its tiles
     __syncwarp();
