@@ -234,7 +234,20 @@ def batch_infer_dataset(dataset, infer_ins, config: dict, round_midi: bool = Fal
             continue
         todo.append((row, audio))
     with concurrent.futures.ThreadPoolExecutor(max_workers=workers) as pool:
-        futures = [pool.submit(load_audio, audio, sr) for _, audio in todo]           # decoding overlaps the GPU work below
+        # decoding overlaps the GPU work below; only a bounded window of decoded recordings is ever held (the reference
+        # streams one file at a time; an unbounded list of futures would keep the whole dataset's audio in host memory)
+        import collections
+        window = max(2 * workers, 4)
+        pending: 'collections.deque' = collections.deque()
+        it = iter(todo)
+
+        def refill():
+            while len(pending) < window:
+                nxt = next(it, None)
+                if nxt is None:
+                    return
+                pending.append((nxt[0], pool.submit(load_audio, nxt[1], sr)))
+
         group: List[Tuple[dict, np.ndarray]] = []
         frames = 0
 
@@ -245,8 +258,11 @@ def batch_infer_dataset(dataset, infer_ins, config: dict, round_midi: bool = Fal
                     row['note_seq'], row['note_dur'] = row_notes(row['ph_dur'], row['ph_num'], note_timeline(offsets, segments), round_midi)
             group, frames = [], 0
 
-        for (row, _), fut in zip(todo, futures):
+        refill()
+        while pending:
+            row, fut = pending.popleft()
             wave = fut.result()
+            refill()
             t = 1 + len(wave) // 512
             if group and frames + t > max_frames_per_batch:
                 flush()

@@ -163,3 +163,21 @@ def test_silence_is_log_clamp(tmp_path):
     ins, _ = _plugin('two_head', tmp_path)
     units = ins.preprocess(np.zeros(44100, dtype=np.float32))['units']
     assert torch.all(units == float(np.log(np.float32(1e-5))))
+
+
+def test_two_engines_on_two_devices_in_one_process(tmp_path):
+    """function attributes (dynamic shared-memory opt-in, carveout) and the SM count are per device; the
+    library keeps them per device ordinal, so a second engine on cuda:1 in the same process must work and agree with cuda:0."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two CUDA devices in one process')
+    from some_b200 import plugin
+    config = synth.named_config('two_head')
+    ckpt = synth.write_checkpoint(tmp_path, config, seed=1234)
+    waves = [synth.synth_waveform(800 + i, seconds=s) for i, s in enumerate([1.1, 2.3])]
+    outs = []
+    for dev in ('cuda:0', 'cuda:1'):
+        ins = plugin.MIDIExtractionInference(config=config, model_path=ckpt, device=dev)
+        outs.append(ins.infer(waves))
+    for a, b in zip(*outs):
+        for k in ('note_midi', 'note_dur', 'note_rest'):
+            np.testing.assert_array_equal(a[k], b[k])

@@ -190,7 +190,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
       uint32_t served = 0, spins = 0;
       auto try_tile = [&](int g) -> bool {
         const int j = nxt[g];
-        if (j >= n_tiles || !mbar_try_wait(&p_full[j % 3], (j / 3) & 1)) return false;
+        // p_full[j % 3] is shared with tile j - 3 (the other group's): its phase for tile j may only be polled once the phase
+        // of tile j - 3 has been consumed, otherwise the parity test aliases with the phase before that one
+        if (j >= n_tiles || (j >= 3 && nxt[g ^ 1] <= j - 3)) return false;
+        if (!mbar_try_wait(&p_full[j % 3], (j / 3) & 1)) return false;
         tc_fence_after_sync();
         const int s = j % TC_STAGES, b = j % 3;
         mbar_wait(&v_full[s], (j / TC_STAGES) & 1);
@@ -302,9 +305,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
     };
     // wait on an mbarrier from a point where joining a rendezvous is safe
     auto wait_joining = [&](uint64_t* bar, uint32_t parity) {
+      // warp-uniform decisions only: the lanes poll independently, and a lane that has seen the phase complete must not run
+      // ahead (tcgen05.ld is .sync.aligned) while its siblings enter the rendezvous (bar.sync counts threads)
       uint32_t spins = 0;
-      while (!mbar_try_wait(bar, parity)) {
-        if (*sync_flag) rendezvous(R);
+      while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+        if (__any_sync(0xffffffffu, *sync_flag != 0)) rendezvous(R);
         if (++spins == (1u << 24)) {
           printf("some_b200: attention v8 softmax wait timeout block %d warp %d\n", (int)blockIdx.x, warp);
           __trap();
@@ -431,8 +436,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
     if (lane == 0) atomicAdd(const_cast<int*>(done_cnt), 1);
     {
       uint32_t spins = 0;
-      while (*done_cnt < 8) {
-        if (*sync_flag) rendezvous(R);
+      while (__any_sync(0xffffffffu, *done_cnt < 8)) {
+        if (__any_sync(0xffffffffu, *sync_flag != 0)) rendezvous(R);
         if (++spins == (1u << 26)) {
           printf("some_b200: attention v8 drain timeout block %d warp %d\n", (int)blockIdx.x, warp);
           __trap();
