@@ -355,6 +355,32 @@ def test_attention_growing_max_forces_rescale(lib):
             r0 += t
 
 
+@pytest.mark.parametrize('outlier', [200, 206, 519, 1023])
+def test_attention_outlier_key_after_the_first_tile(lib, outlier):
+    """The exp pass runs against the group's stale reference maximum and a tile is redone only when its row sum gives an
+    overflow away (attention_tc.cu).  One key far above everything seen so far -- by more than 2^127 in the exponent, so the
+    first attempt produces +inf -- placed in a tile other than a group's first one, at a position handled by the MUFU path
+    (key index % 8 < 6) or by the polynomial path (% 8 in {6, 7}, which must clamp instead of wrapping around)."""
+    torch.manual_seed(9)
+    t = 1100
+    cu = _cu([t])
+    qkv = torch.randn(t, 1536, device=DEV) * 0.5
+    qkv[:, :512] = qkv[:, :512].abs()                         # q > 0, so a key of all + LARGE scores high against every query
+    qkv[outlier, 512:1024] = 40.0                             # score ~ 64 * 0.4 * 40 = 1000  ->  1000 / 8 * log2(e) = 180 > 127
+    qkv = qkv.to(torch.bfloat16)
+    out = torch.full((t, 512), float('nan'), device=DEV, dtype=torch.bfloat16)
+    a = _lib.AttnArgs()
+    a.qkv, a.out = _lib.pair(qkv), _lib.pair(out)
+    a.groups, a.B, a.M, a.cu_frames, a.max_frames = 1, 1, t, cu.data_ptr(), t
+    _lib.check(lib.some_attention_varlen(C.byref(a), stream()))
+    torch.cuda.synchronize()
+    z = qkv.float()
+    q, k, v = (z[:, j * 512:(j + 1) * 512].reshape(t, 8, 64).transpose(0, 1) for j in range(3))
+    ref = torch.nn.functional.scaled_dot_product_attention(q[None], k[None], v[None])[0].transpose(0, 1).reshape(t, 512)
+    assert torch.isfinite(out.float()).all()
+    torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=2e-2)     # every row is (almost) exactly v[outlier]
+
+
 def test_mel_matches_torch_stft(lib):
     from some_b200 import synth
     from some_b200.engine import Engine

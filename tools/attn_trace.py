@@ -18,7 +18,7 @@ def build():
     src = os.path.join(ROOT, 'some_b200', 'csrc')
     subprocess.check_call(['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
                            '-DSOME_ATTN_TRACE', *os.environ.get('ATTN_TRACE_FLAGS', '').split(), '-Xcompiler', '-fPIC', '-shared', '-o', OUT,
-                           os.path.join(src, 'attention_tc.cu'), os.path.join(src, 'host_common.cu'), '-lcudart'])
+                           os.environ.get('ATTN_TRACE_SRC', os.path.join(src, 'attention_tc.cu')), os.path.join(src, 'host_common.cu'), '-lcudart'])
 
 
 def run():
@@ -54,6 +54,12 @@ def run():
         e = t[g, j] - t0
         m = t[2, j] - t0
         print(f'{j:4d} |  {"AB"[g]}: {e[0]:7d} {e[1]:7d} {e[2]:7d} {e[3]:7d} | {m[0]:7d} {m[1]:7d} {m[2]:7d} {m[3]:7d}')
+    if t[3].any():   # v8 builds: role 3 = extra points (group started waiting for S_j | MMA: V_j ready | K_{j+3} ready)
+        print('tile | group started waiting | mma: p_full_seen -> V ready -> PV issued -> K(j+3) ready -> QK issued')
+        for j in range(4, min(n, 24)):
+            x = t[3, j] - t0
+            m = t[2, j] - t0
+            print(f'{j:4d} | {x[0]:7d} | {m[1]:7d} {x[1] - m[1]:6d} {m[2] - x[1]:6d} {x[2] - m[2]:6d} {m[3] - x[2]:6d}')
     for g in range(2):
         js = np.arange(g + 4, min(n, 40), 2)
         per = np.diff(t[g, js, 0]).mean()

@@ -1,3 +1,4 @@
+// EXPERIMENTAL (built only by tools/ab_bench.py --src): attention v9 = the shipped kernel without the row-maximum pass.
 // K-attn (tcgen05): per-clip (var-len) multi-head self-attention softmax(Q K^T / 8) V, no mask, 8 heads x 64
 // (base_attention.py:34-45; conform_blocke never forwards a mask: Gconform.py:83-84,133).
 //
@@ -16,14 +17,12 @@
 //             O[j & 1] += P_j V_j (M128 N64 K16 x4, A = P from TENSOR MEMORY, B = V MN-major); QK_{j+2} right behind PV_j
 //   warps 2-5 softmax group 0 (even tiles), warps 6-9 group 1 (odd tiles); thread = query row (TMEM lane): online
 //             softmax in base 2 (packed f32x2 scale/sum, ex2.approx), P -> bf16 pairs -> tcgen05.st over the first half of
-//             the S buffer just read.  There is NO row-maximum pass in the steady state: the exp pass runs against the
-//             group's stale reference maximum (exact: the final division by the row sum removes the reference) and a tile
-//             whose row sum exceeds 2^14 (some p > 2^8, +inf on overflow) is redone the slow way -- row maximum, O rescaled
-//             in TMEM (tcgen05.ld / st), l rescaled, exp pass again (S_j is intact: P is stored last).  The first tile of a
-//             group takes the slow path.  warp 2 also owns the TMEM allocation: S0 | S1 | O0 | O1, 64 columns each.
+//             the S buffer just read.  O stays in TMEM and is rescaled (tcgen05.ld / st) only when some row maximum of
+//             the warp grew by more than 2^8 ("lazy rescale": otherwise the stale maximum is kept, P <= 256, exact after
+//             the final division by the row sum).  warp 2 also owns the TMEM allocation: S0 | S1 | O0 | O1, 64 columns each.
 // Rows of K/V beyond the clip end are masked (p = 0); rows beyond M are zero-filled by TMA.
-#include "host_common.h"
-#include "sm100_ptx.cuh"
+#include "../../some_b200/csrc/host_common.h"
+#include "../../some_b200/csrc/sm100_ptx.cuh"
 
 #include "../../include/some_b200.h"
 
@@ -57,7 +56,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ void exp2_poly2(uint64_t y2, float& p0, float& p1) {
   float a, b;
   f2_unpack(y2, a, b);
-  a = fminf(fmaxf(a, -126.f), 126.f);   // upper clamp: an overflowing score must show up as a huge p (it is detected from the row sum)
+  a = fminf(fmaxf(a, -126.f), 126.f);   // upper clamp: an overflowing score must show up as a huge p (v9 detects it from the row sum)
   b = fminf(fmaxf(b, -126.f), 126.f);
   const uint64_t y = f2_pack(a, b);
   const uint64_t xf = f2_add(y, f2_pack(12582912.f, 12582912.f));
@@ -260,7 +259,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
       }
 #endif
       ATTN_TRACE(g, j, 0);
-      // The exp pass runs against the STALE reference m_used WITHOUT looking for this tile's maximum first.  That is exact as
+      // v9: the exp pass runs against the STALE reference m_used WITHOUT looking for this tile's maximum first.  That is exact as
       // long as nothing overflows (the final division by the row sum removes the reference).  A tile whose row sum exceeds 2^14
       // (=> some p > 2^8; +inf when a score sits more than 2^126 above the reference) is redone the slow way: row maximum, O and
       // l brought to the new reference, exp pass again -- S_j is still intact in tensor memory because P is stored last.
@@ -280,7 +279,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
             if (valid == TC_BN) {  // eight independent chains (a single fmax chain is 32 dependent FMNMX3)
               float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
               float m4 = -INFINITY, m5 = -INFINITY, m6 = -INFINITY, m7 = -INFINITY;
-#pragma unroll
+    #pragma unroll
               for (int i = 0; i < 32; i += 8) {
                 m0 = fmaxf(m0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
                 m1 = fmaxf(m1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
@@ -293,7 +292,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
               }
               mx = fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), fmaxf(fmaxf(m4, m5), fmaxf(m6, m7)));
             } else {
-#pragma unroll
+    #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 if (i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
                 if (32 + i < valid) mx = fmaxf(mx, __uint_as_float(u[i]));
