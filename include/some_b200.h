@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SOME_B200_VERSION 200
+#define SOME_B200_VERSION 201
 
 #ifndef __CUDA_RUNTIME_H__
 typedef struct CUstream_st* cudaStream_t;
@@ -44,6 +44,12 @@ typedef struct CUstream_st* cudaStream_t;
 
 int some_version(void);
 const char* some_last_error(void);
+/* Programmatic dependent launch for the CALLING thread's subsequent launches of the trunk kernels (some_gemm, some_layernorm,
+ * some_attention_varlen, some_dwconv_bn_silu, some_bound_head, and through them some_forward): a kernel may become resident and
+ * run its prologue while its predecessor in the stream is still running; it touches activations only after the predecessor has
+ * completed (griddepcontrol.wait).  Pays on small batches (a step is ~70 dependent launches of a few microseconds each); works
+ * under stream capture.  Returns the previous setting.  No reference counterpart. */
+int some_set_pdl(int on);
 
 /* ---- K-mel: modules/rmvpe/spec.py:38-72 (F.pad 1024/1024, torch.stft n_fft 2048 hop 512 periodic Hann,
  * abs, mel_basis matmul, log(clamp 1e-5)) + the transpose at inference/me_infer.py:31.

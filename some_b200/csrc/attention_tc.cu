@@ -157,6 +157,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();     // programmatic dependent launch (host_common.h): qkv is read only after the producing GEMM has completed
+  griddep_wait();
 
 #ifdef SOME_ATTN_DIAG_NOMMA
   if (warp < 2) {
@@ -480,6 +482,6 @@ extern "C" int some_attention_varlen(const some_attn_args* a, cudaStream_t strea
   const long long gx = 1ll * p.tiles_per_clip * a->B;
   SOME_REQUIRE(gx < (1ll << 31), "some_attention_varlen: grid too large");
   dim3 grid(static_cast<unsigned>(gx), SOME_HEADS, a->groups);
-  attention_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+  launch_pdl(attention_tc_kernel, grid, dim3(TC_THREADS), TC_SMEM, stream, maps[0], maps[1], maps[2], maps[3], p);
   return check_launch("some_attention_varlen");
 }

@@ -191,6 +191,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();
+  griddep_wait();
 
   if (warp == 0) {
     if (elect_one_sync()) {
@@ -591,6 +593,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   cluster_sync_all();   // barrier inits + TMEM allocation of BOTH CTAs visible before any remote arrive / multicast
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();     // programmatic dependent launch: the next kernel may start its own prologue ...
+  griddep_wait();       // ... and this one touches activations only after its predecessor has completed
 
   if (warp == 0) {
     if (elect_one_sync()) {
@@ -847,7 +851,7 @@ static int launch_gemm_pair(const CUtensorMap* maps, const EpiMaps& em, const Ge
   const int tiles = num_m * (p.N / PAIR_BN) * p.groups;
   int pairs = num_sms() / 2;
   if (tiles < pairs) pairs = tiles;
-  kern<<<2 * pairs, GEMM_THREADS, PairCfg<EPI>::SMEM, stream>>>(maps[0], maps[1], maps[2], maps[3], em, p);
+  launch_pdl(kern, dim3(2 * pairs), dim3(GEMM_THREADS), PairCfg<EPI>::SMEM, stream, maps[0], maps[1], maps[2], maps[3], em, p);
   return check_launch("some_gemm(pair)");
 }
 
@@ -867,7 +871,7 @@ static int launch_gemm(const CUtensorMap* maps, const GemmParams& p, cudaStream_
   const int tiles = num_m * num_n * p.groups;
   int grid = num_sms();
   if (tiles < grid) grid = tiles;
-  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+  launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), S::TOTAL, stream, maps[0], maps[1], maps[2], maps[3], p);
   return check_launch("some_gemm");
 }
 

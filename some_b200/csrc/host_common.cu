@@ -123,9 +123,17 @@ int num_sms() {
   return n[dev];
 }
 
+static thread_local bool g_pdl = false;   // per launching thread (an engine's launches are serialised on one thread at a time)
+bool pdl_enabled() { return g_pdl; }
+
 }  // namespace some
 
 extern "C" {
 int some_version(void) { return SOME_B200_VERSION; }
+int some_set_pdl(int on) {
+  const int was = some::g_pdl ? 1 : 0;
+  some::g_pdl = on != 0;
+  return was;
+}
 const char* some_last_error(void) { return some::g_err; }
 }

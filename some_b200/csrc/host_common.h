@@ -28,6 +28,26 @@ constexpr int kMaxDevices = 64;
 int device_index();
 int num_sms();
 
+// Programmatic dependent launch (some_set_pdl): a kernel launched through launch_pdl() may become resident while its
+// predecessor in the stream is still running; it executes its prologue (barrier init, TMEM allocation, tensor-map prefetch) and
+// blocks in griddep_wait() -- which every such kernel calls before its first access to activations -- until the predecessor has
+// completed and flushed.  Pays on small batches, where a step is ~70 dependent launches of a few microseconds each.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 #define SOME_REQUIRE(cond, ...)      \
   do {                               \
     if (!(cond)) {                   \

@@ -88,6 +88,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
   const int grp = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int row0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * LN_RPW;
+  griddep_launch();   // programmatic dependent launch (host_common.h)
+  griddep_wait();
   if (row0 >= p.M) return;
   float v[LN_RPW][16];
 #pragma unroll
@@ -171,6 +173,8 @@ bound_head_kernel(const float* __restrict__ x, const float* __restrict__ gamma, 
                   const float* __restrict__ w, float bias, int M, float* __restrict__ bounds) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  griddep_launch();
+  griddep_wait();
   if (row >= M) return;
   float y[16];
   ln_row(x + (size_t)row * D, gamma, beta, lane, y);
@@ -248,6 +252,8 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const DwParams p) {
 #pragma unroll
   for (int k = 0; k < SOME_CONV_K; ++k) w[k] = __ldg(reinterpret_cast<const unsigned long long*>(p.w[grp] + k * D + c));
   const uint64_t bb = __ldg(reinterpret_cast<const unsigned long long*>(p.b[grp] + c));
+  griddep_launch();   // programmatic dependent launch: the taps (weights) are loaded, activations only after the wait
+  griddep_wait();
 
   int t = blockIdx.x, buf = 0;
   if (t < p.num_tiles) prefetch(t, 0);
@@ -307,7 +313,7 @@ extern "C" int some_layernorm(const some_ln_args* a, cudaStream_t stream) {
   }
   p.M = a->M;
   dim3 grid((a->M + 8 * LN_RPW - 1) / (8 * LN_RPW), a->groups);
-  layernorm_kernel<<<grid, 256, 0, stream>>>(p);
+  launch_pdl(layernorm_kernel, grid, dim3(256), 0, stream, p);
   return check_launch("some_layernorm");
 }
 
@@ -344,7 +350,7 @@ extern "C" int some_bound_head(const float* x, const float* gamma, const float* 
                                int M, float* bounds, cudaStream_t stream) {
   SOME_REQUIRE(x && gamma && beta && w && bounds, "some_bound_head: null pointer");
   if (M <= 0) return 0;
-  bound_head_kernel<<<(M + 7) / 8, 256, 0, stream>>>(x, gamma, beta, w, bias, M, bounds);
+  launch_pdl(bound_head_kernel, dim3((M + 7) / 8), dim3(256), 0, stream, x, gamma, beta, w, bias, M, bounds);
   return check_launch("some_bound_head");
 }
 
@@ -370,6 +376,6 @@ extern "C" int some_dwconv_bn_silu(const some_dwconv_args* a, cudaStream_t strea
   if (per_cb < 1) per_cb = 1;
   p.ctas_per_cb = static_cast<int>(nt < per_cb ? nt : per_cb);
   dim3 grid(p.ctas_per_cb, D / DW_C, a->groups);
-  dwconv_kernel<<<grid, 256, 0, stream>>>(p);
+  launch_pdl(dwconv_kernel, grid, dim3(256), 0, stream, p);
   return check_launch("some_dwconv_bn_silu");
 }

@@ -92,6 +92,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// griddep_launch(): this CTA no longer holds back the launch of the next kernel in the stream (it may become resident and run
+// its prologue).  griddep_wait(): blocks until the PREVIOUS kernel has completed and its writes are visible; a no-op when the
+// kernel was launched without the programmatic-serialization attribute.  Everything before the wait must not touch activations.
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------ proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -99,6 +99,8 @@ class Engine:
         self._graphs: dict = {}
         self._graph_seen: dict = {}
         self.use_graphs = os.environ.get('SOME_B200_GRAPHS', '1') != '0'
+        # programmatic dependent launch of the trunk kernels: 'small' = chunks that also replay as a CUDA graph, 'all', 'off'
+        self.pdl = {'0': 'off', 'off': 'off', '1': 'all', 'all': 'all'}.get(os.environ.get('SOME_B200_PDL', 'small'), 'small')
         self._corrected: set = set()
         self.bias_correction = os.environ.get('SOME_B200_BIAS_CORRECTION', '1') != '0'
         if self.bias_correction:
@@ -507,16 +509,23 @@ class Engine:
             note_midi = o[4 * bc + 4 * mc:4 * bc + 8 * mc].view(torch.float32)
             note_rest = o[4 * bc + 8 * mc:]
             mel_f32 = torch.empty((mc, 80), dtype=torch.float32, device=dev) if return_intermediates else None
+            pdl = self.pdl == 'all' or (self.pdl == 'small' and mc <= self.GRAPH_MAX_FRAMES)
+
             def launch_chunk():
                 self.run_mel(wave_d[lo:], tab_dev[:bc], tab_dev[bc:2 * bc], cu_d, bc, max_frames, mel_f32, ws.units)
-                self.run_trunk(ws, mc, bc, cu_d, max_frames, 'softmax' if quantized else 'sigmoid')
+                was = self.lib.some_set_pdl(1) if pdl else 0    # programmatic dependent launch of the trunk kernels
+                try:
+                    self.run_trunk(ws, mc, bc, cu_d, max_frames, 'softmax' if quantized else 'sigmoid')
+                finally:
+                    if pdl:
+                        self.lib.some_set_pdl(was)
                 self.run_decode(ws, mc, bc, cu_d, note_count, quantized, out=(note_midi, note_dur, note_rest))
 
             if mc <= self.GRAPH_MAX_FRAMES and self.use_graphs and self.prof is None and not return_intermediates:
                 # small batches are launch-bound (~56 launches of a few microseconds each): replay them as ONE CUDA graph,
                 # keyed by everything the captured kernel arguments depend on
                 self._graphed((wave_d.data_ptr() + 4 * lo, tab_dev.data_ptr(), cu_d.data_ptr(), o.data_ptr(), ws.serial, bc, mc,
-                               max_frames, bool(quantized), self.ln_fold), launch_chunk)
+                               max_frames, bool(quantized), self.ln_fold, pdl), launch_chunk)
             else:
                 launch_chunk()
             if return_intermediates:

@@ -124,6 +124,44 @@ def test_ln_fold_matches_standalone_layernorm(tmp_path):
     assert float((out[True][1] - out[False][1]).abs().max()) < 6e-3
 
 
+def test_programmatic_dependent_launch_is_bit_identical(tmp_path):
+    """some_set_pdl: the trunk kernels launched with the programmatic-serialization attribute (each one may start its prologue
+    while its predecessor is still running and blocks in griddepcontrol.wait before touching activations) compute exactly what
+    the fully serialised launches compute -- eagerly and when the chunk replays as a CUDA graph (the small-batch path)."""
+    ins, _ = _plugin('two_head', tmp_path)
+    eng = ins.model
+    frames = [300, 41, 129, 1]
+    m, b = sum(frames), len(frames)
+    cu = torch.tensor(np.cumsum([0] + frames), dtype=torch.int32, device=eng.device)
+    ws = eng.workspace(m)
+    torch.manual_seed(1)
+    ws.units[:m].copy_(torch.randn(m, 80, device=eng.device) * 3 - 4)
+    out = {}
+    for on in (0, 1):
+        ws.probs.fill_(float('nan'))
+        ws.bounds.fill_(float('nan'))
+        was = eng.lib.some_set_pdl(on)
+        try:
+            for _ in range(3):                       # back to back: the overlap window is between consecutive kernels
+                eng.run_trunk(ws, m, b, cu, max(frames), 'sigmoid')
+        finally:
+            assert eng.lib.some_set_pdl(was) == on
+        torch.cuda.synchronize()
+        out[on] = (ws.probs[:m].clone(), ws.bounds[:m].clone())
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    assert not torch.isnan(out[1][0]).any()
+    # end to end through the graph-replayed small-chunk path (one ~10 s clip), PDL on (default 'small') vs off
+    clip = [synth.synth_waveform(321, seconds=9.0)]
+    notes = {}
+    for mode in ('off', 'small'):
+        eng.pdl = mode
+        for _ in range(3):                           # eager, capture, replay
+            notes[mode] = ins.infer(clip)
+    eng.pdl = 'small'
+    for k in ('note_midi', 'note_dur', 'note_rest'):
+        np.testing.assert_array_equal(notes['off'][0][k], notes['small'][0][k])
+
+
 def test_chunked_pipeline_equals_single_chunk(tmp_path):
     """infer() cuts big batches into pipeline chunks (staging / H2D overlap); results must not depend on it."""
     ins, _ = _plugin('two_head', tmp_path)

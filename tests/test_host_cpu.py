@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), (declared ^ set(_lib.EXPORTS))
     for name in declared:
         assert hasattr(lib, name), f'{name} declared in include/some_b200.h but not exported'
-    assert lib.some_version() == 200
+    assert lib.some_version() == 201
     assert lib.some_last_error() is not None
 
 

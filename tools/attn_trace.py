@@ -54,12 +54,11 @@ def run():
         e = t[g, j] - t0
         m = t[2, j] - t0
         print(f'{j:4d} |  {"AB"[g]}: {e[0]:7d} {e[1]:7d} {e[2]:7d} {e[3]:7d} | {m[0]:7d} {m[1]:7d} {m[2]:7d} {m[3]:7d}')
-    if t[3].any():   # v8 builds: role 3 = extra points (group started waiting for S_j | MMA: V_j ready | K_{j+3} ready)
-        print('tile | group started waiting | mma: p_full_seen -> V ready -> PV issued -> K(j+3) ready -> QK issued')
-        for j in range(4, min(n, 24)):
+    if t[3].any():   # v8 builds: role 3 = extra points
+        print('tile | group started waiting for S_j | producer: waits for the slot of V_j, issues the load | mma thread: V_j seen | mma p_full_seen(j)')
+        for j in range(4, min(n, 30)):
             x = t[3, j] - t0
-            m = t[2, j] - t0
-            print(f'{j:4d} | {x[0]:7d} | {m[1]:7d} {x[1] - m[1]:6d} {m[2] - x[1]:6d} {x[2] - m[2]:6d} {m[3] - x[2]:6d}')
+            print(f'{j:4d} | {x[0]:7d} | {x[3]:7d} {x[2]:7d} | {x[1]:7d}  (issue -> seen {x[1] - x[2]:6d}) | {t[2, j, 1] - t0:7d}')
     for g in range(2):
         js = np.arange(g + 4, min(n, 40), 2)
         per = np.diff(t[g, js, 0]).mean()

@@ -130,7 +130,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
   const int n_tiles = (T + TC_BN - 1) / TC_BN;
 #ifdef SOME_ATTN_TRACE
   const bool trace_on = g_attn_trace != nullptr && blockIdx.x == 7 && blockIdx.y == 3 && blockIdx.z == 0 &&
-                        (lane == 0 || warp == 1) && (warp == 1 || warp == 2 || warp == 6);
+                        (lane == 0 || warp <= 1) && (warp <= 2 || warp == 6);
 #endif
 
   if (threadIdx.x == 0) {
@@ -181,7 +181,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
       };
       auto load_v = [&](int t) {
         const int s = t % TC_STAGES;
+        ATTN_TRACE(3, t, 3);                       // producer starts waiting for the slot of V_t
         mbar_wait(&v_empty[s], ((t / TC_STAGES) & 1) ^ 1);
+        ATTN_TRACE(3, t, 2);                       // V_t load issued
         mbar_arrive_expect_tx(&v_full[s], TC_KTILE);
         tma_load_2d(sV + s * TC_KTILE, tmkv, &v_full[s], 2 * SOME_DIM + head * 64, row_begin + t * TC_BN);
       };
@@ -261,6 +263,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq0, const __grid_const
         nxt[g] = j + 2;
         --remaining;
         wait_v(j + 2);                              // operands of this group's next service (see above)
+        ATTN_TRACE(3, j + 2, 1);                    // V_{j+2} seen in shared memory (an upper bound of its arrival time)
         wait_k(j + 5);
         return true;
       };

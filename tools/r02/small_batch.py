@@ -17,10 +17,14 @@ def pin(w):
 cases = {'1x10s': [pin(synth.synth_waveform(11, seconds=10.0))], '1x30s': [pin(synth.synth_waveform(12, seconds=30.0))],
          '4x10s': [pin(synth.synth_waveform(20 + i, seconds=10.0)) for i in range(4)]}
 out = {}
+MODES = [(False, False, 'off'), (True, False, 'off'), (True, False, 'small'), (True, True, 'off'), (True, True, 'small')]
 for name, clips in cases.items():
     secs = sum(len(c) for c in clips) / synth.SR
-    for graphs in (False, True):
+    for graphs, fold, pdl in MODES:
         eng.use_graphs = graphs
+        eng.pdl = pdl
+        if eng.ln_fold != fold:
+            eng.set_ln_fold(fold)
         ref = ins.infer(clips)
         for _ in range(4):
             res = ins.infer(clips)
@@ -37,7 +41,9 @@ for name, clips in cases.items():
         ws = eng.workspace(m); nc = torch.empty(b, dtype=torch.int32, device=dev)
         def step():
             eng.run_mel(wave, tab[:b], tab[b:], cu_d, b, mf, None, ws.units)
+            was = eng.lib.some_set_pdl(1 if pdl != 'off' else 0)
             eng.run_trunk(ws, m, b, cu_d, mf, 'sigmoid')
+            eng.lib.some_set_pdl(was)
             eng.run_decode(ws, m, b, cu_d, nc, False)
         for _ in range(3): step()
         torch.cuda.synchronize()
@@ -53,7 +59,7 @@ for name, clips in cases.items():
         for _ in range(20): run()
         e1.record(); torch.cuda.synchronize()
         dms = e0.elapsed_time(e1) / 20
-        out[f'{name} graphs={int(graphs)}'] = {'e2e_ms': round(ms, 3), 'e2e_rtf': round(secs / (ms / 1e3)), 'device_ms': round(dms, 3),
+        out[f'{name} graphs={int(graphs)} fold={int(fold)} pdl={pdl}'] = {'e2e_ms': round(ms, 3), 'e2e_rtf': round(secs / (ms / 1e3)), 'device_ms': round(dms, 3),
                                                'device_rtf': round(secs / (dms / 1e3)), 'same_notes': same}
-        print(name, 'graphs', graphs, f'e2e {ms:.3f} ms ({secs / (ms / 1e3):.0f} x RT)  device {dms:.3f} ms ({secs / (dms / 1e3):.0f} x RT)  same={same}')
+        print(name, 'graphs', graphs, 'fold', fold, 'pdl', pdl, f'e2e {ms:.3f} ms ({secs / (ms / 1e3):.0f} x RT)  device {dms:.3f} ms ({secs / (dms / 1e3):.0f} x RT)  same={same}')
 print(json.dumps(out))
