@@ -389,6 +389,17 @@ class Engine:
             self._tp = concurrent.futures.ThreadPoolExecutor(max_workers=min(8, max(2, cores // (2 * local_world))))
         return self._tp
 
+    def slab_layout_cached(self, lens: Sequence[int]):
+        """slab_layout memoised on the clip lengths (a data-parallel step derives every rank's layout on every rank)."""
+        key = tuple(int(x) for x in lens)
+        cache = self.__dict__.setdefault('_layout_cache', {})
+        hit = cache.get(key)
+        if hit is None:
+            if len(cache) >= 256:
+                cache.clear()
+            hit = cache[key] = self.slab_layout(key)
+        return hit
+
     def slab_layout(self, lens: Sequence[int]):
         """Deterministic layout of the packed note slab of a batch with these clip lengths: per pipeline chunk
         (c0, c1, byte offset, clips, frames) and the total size.  Chunk slab = [counts i32 [bc] | dur i32 [mc] | midi f32 [mc]
@@ -663,16 +674,23 @@ class Engine:
         return out
 
     def unpack(self, cu, nc, nm, nd, nr, extra=None) -> List[Dict[str, np.ndarray]]:
-        dur_s = nd * self.timestep     # me_infer.py:95: int64 * python float -> float64; int32 * float gives the same float64s
-        rest_b = nr.astype(bool)
-        midi = nm.copy()                                     # the pinned staging buffer is reused by the next call
-        first, count = cu[:-1].tolist(), nc.tolist()
+        # The slab has room for one note per FRAME (notes of clip j start at row cu[j]); only ~1 row in 5 is used.  Gather the
+        # used rows first (three fancy-index copies of `total` elements: they also detach the result from the pinned landing
+        # buffer, which the next call reuses) and convert only those.
+        count = np.asarray(nc, dtype=np.int64)
+        ends = np.cumsum(count)
+        total = int(ends[-1]) if len(ends) else 0
+        starts = ends - count
+        rows = np.repeat(np.asarray(cu[:-1], dtype=np.int64) - starts, count) + np.arange(total, dtype=np.int64)
+        dur_s = nd[rows] * self.timestep   # me_infer.py:95: int64 * python float -> float64; int32 * float gives the same float64s
+        rest_b = nr[rows].astype(bool)
+        midi = nm[rows]
+        lo, hi = starts.tolist(), ends.tolist()
         if extra is None:
-            return [{'note_midi': midi[r0:r0 + n], 'note_dur': dur_s[r0:r0 + n], 'note_rest': rest_b[r0:r0 + n]}
-                    for r0, n in zip(first, count)]
+            return [{'note_midi': midi[a:b], 'note_dur': dur_s[a:b], 'note_rest': rest_b[a:b]} for a, b in zip(lo, hi)]
         out = []
-        for i, (r0, n) in enumerate(zip(first, count)):
-            e1 = int(cu[i + 1])
-            out.append({'note_midi': midi[r0:r0 + n], 'note_dur': dur_s[r0:r0 + n], 'note_rest': rest_b[r0:r0 + n],
+        for i, (a, b) in enumerate(zip(lo, hi)):
+            r0, e1 = int(cu[i]), int(cu[i + 1])
+            out.append({'note_midi': midi[a:b], 'note_dur': dur_s[a:b], 'note_rest': rest_b[a:b],
                         'mel': extra[0][r0:e1].numpy(), 'probs': extra[1][r0:e1].numpy(), 'bounds': extra[2][r0:e1].numpy()})
         return out

@@ -341,3 +341,13 @@ def test_engine_unpack_slab_reads_the_decode_slab_format():
         assert b['note_midi'].dtype == np.float32 and b['note_dur'].dtype == np.float64 and b['note_rest'].dtype == bool
         for k in a:
             np.testing.assert_array_equal(a[k], b[k])
+    # the results own their data (the pinned landing buffer the slab lives in is reused by the next call)
+    snapshot = [{k: v.copy() for k, v in r.items()} for r in back]
+    host[:] = 0xFF
+    for a, b in zip(snapshot, back):
+        for k in a:
+            np.testing.assert_array_equal(a[k], b[k])
+    assert eng.slab_layout_cached(lens) is eng.slab_layout_cached(list(lens))           # memoised on the lengths
+    cu3, layout3, nbytes3 = eng.slab_layout_cached(lens)
+    np.testing.assert_array_equal(cu3, cu)
+    assert layout3 == layout and nbytes3 == nbytes
