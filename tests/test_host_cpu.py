@@ -351,3 +351,47 @@ def test_engine_unpack_slab_reads_the_decode_slab_format():
     cu3, layout3, nbytes3 = eng.slab_layout_cached(lens)
     np.testing.assert_array_equal(cu3, cu)
     assert layout3 == layout and nbytes3 == nbytes
+
+
+def test_sharded_results_are_lazy_per_rank_and_survive_buffer_reuse():
+    """dist.ShardedResults (what infer_sharded returns on the NCCL path): a rank's slab is unpacked when one of ITS clips is first
+    touched; the slabs live in a landing buffer the next call overwrites, so infer_sharded materialises whatever is still lazy
+    before it reuses the buffer (here: emulated with the same calls)."""
+    eng = _bare_engine()
+    lens = [[70000, 512 * 40 + 7], [90000, 300, 0]]                 # two ranks' shards
+    shards = [[0, 3], [1, 2, 4]]                                     # global clip index of each shard entry
+    layouts = [eng.slab_layout_cached(l) for l in lens]
+    nbytes = max(l[2] for l in layouts)
+    landing = np.zeros(2 * nbytes, dtype=np.uint8)
+    notes = {}
+    for r, (cu, layout, _) in enumerate(layouts):
+        fake = [_fake_notes(n + 17 * r) for n in lens[r]]
+        for i, f in zip(shards[r], fake):
+            notes[i] = f
+        for c0, c1, off, bc, mc in layout:
+            frames = [int(cu[i + 1] - cu[i]) for i in range(c0, c1)]
+            slab = sdist.pack_results(fake[c0:c1], frames, 4 * bc + 9 * mc, 512 / 44100)
+            landing[r * nbytes + off:r * nbytes + off + slab.size] = slab
+    calls = []
+
+    def unpacker(r):
+        cu_r, layout_r, _ = layouts[r]
+
+        def run():
+            calls.append(r)
+            return list(zip(shards[r], eng.unpack_slab(landing[r * nbytes:(r + 1) * nbytes], cu_r, layout_r)))
+        return run
+
+    owner = [0, 1, 1, 0, 1]
+    res = sdist.ShardedResults(5, owner, [unpacker(0), unpacker(1)])
+    res._materialise_rank(0)                                         # a rank's own shard is unpacked eagerly
+    assert calls == [0] and len(res) == 5
+    np.testing.assert_array_equal(res[3]['note_midi'], notes[3]['note_midi'])
+    assert calls == [0]                                              # touching an own clip unpacks nothing new
+    res.materialise()                                                # what infer_sharded does before reusing the buffer
+    assert calls == [0, 1]
+    landing[:] = 0xFF                                                # the next call's gather lands
+    for i in range(5):
+        for k in ('note_midi', 'note_dur', 'note_rest'):
+            np.testing.assert_array_equal(res[i][k], notes[i][k])
+    assert calls == [0, 1] and [r['note_midi'].shape for r in res[1:3]] == [notes[1]['note_midi'].shape, notes[2]['note_midi'].shape]
