@@ -5,13 +5,13 @@
 // output bf16 [M, 512] = 'b h t c -> b t (h c)'.  No head-major copies are made: Q/K/V tiles are TMA boxes cut
 // straight out of qkv.
 //
-// CTA = 128 query rows of one (clip, head), 64-key tiles; 2 CTAs per SM (82 KB smem, 256 TMEM columns each).
+// CTA = 128 query rows of one (clip, head), 64-key tiles; 2 CTAs per SM (98 KB smem, 256 TMEM columns each).
 // The kernel is bound by the MUFU pipe (one ex2 per score: 8192 per tile = 512 clk/SM against 256 clk of tensor work),
 // so the design goal is to keep the four XU pipes fed: TWO independent softmax warpgroups per CTA, each owning every
 // other key tile with its OWN running maximum, row sum and O accumulator (split-K inside the CTA, merged once at the
 // end), so that while one group waits for its PV / next QK^T the other one is exponentiating.
 // Roles (320 threads):
-//   warp 0    TMA producer: Q once, then (K_j, V_j) 64-key tiles into a 4-stage ring (128-B swizzle)
+//   warp 0    TMA producer: Q once, then (K_j, V_j) 64-key tiles into a 5-stage ring (128-B swizzle)
 //   warp 1    MMA issuer (one thread):  S_j = Q K_j^T (tcgen05.mma M128 N64 K16 x4, both operands K-major) into S[j & 1];
 //             O[j & 1] += P_j V_j (M128 N64 K16 x4, A = P from TENSOR MEMORY, B = V MN-major); QK_{j+2} right behind PV_j
 //   warps 2-5 softmax group 0 (even tiles), warps 6-9 group 1 (odd tiles); thread = query row (TMEM lane): online
