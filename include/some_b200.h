@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SOME_B200_VERSION 201
+#define SOME_B200_VERSION 202
 
 #ifndef __CUDA_RUNTIME_H__
 typedef struct CUstream_st* cudaStream_t;
@@ -286,6 +286,28 @@ typedef struct {
  * block of that size into the struct (units / probs / bounds included).  Returns 0 / fills *ws on success. */
 uint64_t some_workspace_bytes(int M, int outdim, int ln_fold);
 int some_workspace_carve(void* device_block, uint64_t bytes, int M, int outdim, int ln_fold, some_workspace* ws);
+
+/* ---- Checkpoint packing for hosts that do not use some_b200/weights.py: HOST memory in, HOST memory out, no CUDA call.  The
+ * caller reads the checkpoint (`torch.load(path)['state_dict']`, `model.` prefix: base_infer.py:27-33), calls these, uploads the
+ * results and fills some_model / the table arguments of some_mel_logmel.  (csrc/pack.cu; each mirrors one step of weights.py.)
+ *   some_pack_bf16      fp32 -> bf16, round to nearest even (every GEMM weight: nn.Linear's [N][K] layout is the B operand as is)
+ *   some_pack_glu_rows  rows [out 0..C-1 | gate C..2C-1] -> groups of 32 rows, 16 out rows then their 16 gates: the row order
+ *                       of the GLU producers (pointwise_conv1 base_conv.py:65, glu1 / glu2 Gconform.py:85-87), weights AND biases
+ *   some_pack_dwconv_bn depthwise_conv weight [C][K] + bias and BatchNorm1d running statistics (eval, eps 1e-5) ->
+ *                       taps [K][C] and bias [C] of some_dwconv_bn_silu (base_conv.py:66-67); float64 inside
+ *   some_pack_ln_fold   LayerNorm (gamma, beta) folded into the following Linear for the SOME_EPI_LN_* epilogues:
+ *                       w_out = bf16(W gamma) [N][K] (GLU row order if glu_rows), s_out[n] = sum_k w_out[n][k], b_out = W beta + bias
+ *   some_mel_tables     librosa.filters.mel(sr, 2048, 80, fmin, fmax, htk=True) with the Slaney normalisation (spec.py:22-28) as the
+ *                       sparse tables of some_mel_logmel: mel_start / mel_count [80], mel_weights [80][SOME_MEL_MAXW], the FFT
+ *                       twiddles [SOME_MEL_TW][2] and the periodic Hann window [2048] (spec.py:45); fails if a filter does not fit */
+int some_pack_bf16(const float* src, long long n, uint16_t* dst);
+int some_pack_glu_rows(const void* src, int elem_bytes, int rows, long long row_elems, void* dst);
+int some_pack_dwconv_bn(const float* dw_weight, const float* dw_bias, const float* bn_weight, const float* bn_bias,
+                        const float* bn_mean, const float* bn_var, int channels, int taps, float* out_taps, float* out_bias);
+int some_pack_ln_fold(const float* w, const float* bias, const float* gamma, const float* beta, int n, int k, int glu_rows,
+                      uint16_t* w_out, float* s_out, float* b_out);
+int some_mel_tables(int sample_rate, int n_fft, int n_mels, double fmin, double fmax, int32_t* mel_start, int32_t* mel_count,
+                    float* mel_weights, float* twiddle, float* window);
 
 /* Optional per-launch timing of some_forward (bench.py's roofline pass): CUDA events on the launching stream around every
  * kernel the sequencer enqueues.  The library owns the events; read after the stream has been synchronised. */

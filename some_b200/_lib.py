@@ -13,7 +13,7 @@ EPI_STORE_BF16, EPI_SILU_BF16, EPI_GLU_BF16, EPI_RESID_F32, EPI_GLU_RESID_F32, E
     EPI_SIGMOID_F32, EPI_SOFTMAX_F32, EPI_LN_STORE_BF16, EPI_LN_SILU_BF16, EPI_LN_GLU_BF16, EPI_RESID_F32_LN, \
     EPI_GLU_RESID_F32_LN = range(13)
 LN_SLOTS = 8
-ABI_VERSION = 201
+ABI_VERSION = 202
 K_GEMM, K_ATTENTION, K_LAYERNORM, K_DWCONV, K_BOUND_HEAD, K_ROW_STATS = range(6)
 KERNEL_NAMES = {K_GEMM: 'some_gemm', K_ATTENTION: 'some_attention_varlen', K_LAYERNORM: 'some_layernorm',
                 K_DWCONV: 'some_dwconv_bn_silu', K_BOUND_HEAD: 'some_bound_head', K_ROW_STATS: 'some_row_stats'}
@@ -111,6 +111,11 @@ EXPORTS = {
     'some_version': (C.c_int, []),
     'some_last_error': (C.c_char_p, []),
     'some_set_pdl': (C.c_int, [C.c_int]),
+    'some_pack_bf16': (C.c_int, [_vp, C.c_longlong, _vp]),
+    'some_pack_glu_rows': (C.c_int, [_vp, C.c_int, C.c_int, C.c_longlong, _vp]),
+    'some_pack_dwconv_bn': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
+    'some_pack_ln_fold': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    'some_mel_tables': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     'some_mel_logmel': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   C.c_float, _vp]),
     'some_mel_logmel_keyshift': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _vp, _vp,

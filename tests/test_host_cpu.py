@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), (declared ^ set(_lib.EXPORTS))
     for name in declared:
         assert hasattr(lib, name), f'{name} declared in include/some_b200.h but not exported'
-    assert lib.some_version() == 201
+    assert lib.some_version() == 202
     assert lib.some_last_error() is not None
 
 
@@ -395,3 +395,81 @@ def test_sharded_results_are_lazy_per_rank_and_survive_buffer_reuse():
         for k in ('note_midi', 'note_dur', 'note_rest'):
             np.testing.assert_array_equal(res[i][k], notes[i][k])
     assert calls == [0, 1] and [r['note_midi'].shape for r in res[1:3]] == [notes[1]['note_midi'].shape, notes[2]['note_midi'].shape]
+
+
+# ----------------------------------------------------------------------------- csrc/pack.cu: the C restatement of weights.py
+def _p(a):
+    import ctypes as C
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_c_pack_functions_match_the_python_packing():
+    """Host-only C packing entry points (for non-Python hosts) against what some_b200/weights.py does with torch."""
+    from some_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    # bf16 rounding: RNE, ties, denormals, infinities, NaN
+    x = np.concatenate([rng.standard_normal(4096).astype(np.float32) * 3,
+                        np.array([0.0, -0.0, 1.0, 1.00390625, 1.01171875, 3.3895314e38, np.inf, -np.inf, 1e-40, np.nan], np.float32)])
+    out = np.zeros(x.size, np.uint16)
+    assert lib.some_pack_bf16(_p(x), x.size, _p(out)) == 0
+    ref = torch.from_numpy(x).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    ok = ~np.isnan(x)
+    np.testing.assert_array_equal(out[ok], ref[ok])
+    assert np.isnan(torch.from_numpy(out[~ok].view(np.int16)).view(torch.bfloat16).float().numpy()).all()
+    # GLU row interleave, fp32 weights and bf16-sized elements
+    w = rng.standard_normal((1024, 24)).astype(np.float32)
+    got = np.zeros_like(w)
+    assert lib.some_pack_glu_rows(_p(w), 4, 1024, 24, _p(got)) == 0
+    np.testing.assert_array_equal(got, weights.glu_pack_rows(torch.from_numpy(w)).numpy())
+    b16 = rng.integers(0, 65535, size=(64, 1), dtype=np.uint16)
+    got16 = np.zeros_like(b16)
+    assert lib.some_pack_glu_rows(_p(b16), 2, 64, 1, _p(got16)) == 0
+    np.testing.assert_array_equal(got16, weights.glu_pack_rows(torch.from_numpy(b16.astype(np.int32))).numpy().astype(np.uint16))
+    assert lib.some_pack_glu_rows(_p(w), 4, 1000, 24, _p(got)) != 0 and b'multiple of 32' in lib.some_last_error()
+    # depthwise conv + BatchNorm(eval) folding (BlockWeights: float64 inside, taps transposed to [K][C])
+    c, k = 512, 31
+    dw, db = rng.standard_normal((c, k)).astype(np.float32), rng.standard_normal(c).astype(np.float32)
+    g, be = rng.standard_normal(c).astype(np.float32), rng.standard_normal(c).astype(np.float32)
+    mu, var = rng.standard_normal(c).astype(np.float32), (rng.random(c).astype(np.float32) + 0.1)
+    taps, bias = np.zeros((k, c), np.float32), np.zeros(c, np.float32)
+    assert lib.some_pack_dwconv_bn(_p(dw), _p(db), _p(g), _p(be), _p(mu), _p(var), c, k, _p(taps), _p(bias)) == 0
+    t = lambda a: torch.from_numpy(a)
+    scale = t(g).double() / torch.sqrt(t(var).double() + weights.BN_EPS)
+    np.testing.assert_array_equal(taps, (t(dw).double() * scale[:, None]).t().float().numpy())
+    np.testing.assert_array_equal(bias, ((t(db).double() - t(mu).double()) * scale + t(be).double()).float().numpy())
+    # LayerNorm folding (BlockWeights.fold): rounded weights identical, column sums of the ROUNDED weights, bias = W beta + b
+    n, kk = 1024, 512
+    W, b = (rng.standard_normal((n, kk)) / 22).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+    gam, bet = (1 + 0.1 * rng.standard_normal(kk)).astype(np.float32), (0.1 * rng.standard_normal(kk)).astype(np.float32)
+    for glu in (0, 1):
+        pack = weights.glu_pack_rows if glu else (lambda z: z)
+        w_out, s_out, b_out = np.zeros((n, kk), np.uint16), np.zeros(n, np.float32), np.zeros(n, np.float32)
+        assert lib.some_pack_ln_fold(_p(W), _p(b), _p(gam), _p(bet), n, kk, glu, _p(w_out), _p(s_out), _p(b_out)) == 0
+        w64 = t(W).double()
+        wf = pack((w64 * t(gam).double()[None, :]).float()).to(torch.bfloat16)
+        np.testing.assert_array_equal(w_out, wf.view(torch.int16).numpy().view(np.uint16))
+        np.testing.assert_array_equal(s_out, wf.double().sum(dim=1).float().numpy())
+        np.testing.assert_allclose(b_out, pack((w64 @ t(bet).double() + t(b).double()).float()).numpy(), rtol=0, atol=1e-6)
+
+
+def test_c_mel_tables_match_the_python_tables():
+    """some_mel_tables (librosa.filters.mel restated in C, float64) against weights.mel_tables (numpy / torch restatement that is
+    itself pinned to the reference's basis by tests/golden): identical sparsity, values to the last float32 ulp or two."""
+    from some_b200 import _lib
+    lib = _lib.load()
+    cfg = synth.named_config('two_head')
+    ref = weights.mel_tables(cfg, 'cpu')
+    start, count = np.zeros(80, np.int32), np.zeros(80, np.int32)
+    w = np.full((80, _lib.MEL_MAXW), np.nan, np.float32)
+    tw, win = np.zeros((_lib.MEL_TW, 2), np.float32), np.zeros(2048, np.float32)
+    rc = lib.some_mel_tables(cfg['audio_sample_rate'], cfg['win_size'], cfg['units_dim'], float(cfg['fmin']), float(cfg['fmax']),
+                             _p(start), _p(count), _p(w), _p(tw), _p(win))
+    assert rc == 0, lib.some_last_error()
+    np.testing.assert_array_equal(start, ref['mel_start'].numpy())
+    np.testing.assert_array_equal(count, ref['mel_count'].numpy())
+    np.testing.assert_allclose(w, ref['mel_weights'].numpy(), rtol=3e-7, atol=1e-12)
+    np.testing.assert_allclose(tw, ref['twiddle'].numpy(), rtol=0, atol=6e-8)
+    np.testing.assert_allclose(win, ref['window'].numpy(), rtol=0, atol=2e-7)
+    assert lib.some_mel_tables(44100, 1024, 80, 40.0, 8000.0, _p(start), _p(count), _p(w), _p(tw), _p(win)) != 0
+    assert lib.some_mel_tables(44100, 2048, 80, 40.0, 20000.0, _p(start), _p(count), _p(w), _p(tw), _p(win)) != 0   # filters beyond bin 371
